@@ -1,0 +1,154 @@
+/* gpb200.h -- C-ABI of the B200-native exact-GP / SVGP engine (libgpb200.so).
+ *
+ * Drop-in boundary for the GPflow model path that PortfolioOptGP drives.
+ * The reference has no FFI of its own (it is pure Python on GPflow 2.9.1 / TensorFlow-CPU); every
+ * entry point below therefore cites the reference call site and the GPflow routine whose arithmetic
+ * it replaces.  Paths are relative to the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices fp64, row-major, leading dimension in elements;
+ *   - pointers named d_* are DEVICE pointers on the handle's device (borrowed for the call, or for
+ *     the lifetime of the binding for gpb_gpr_set_data); h_* are HOST pointers;
+ *   - every call returns 0 on success, >0 = LAPACK-style index (1-based) of the first non-positive
+ *     Cholesky pivot (GPflow/TF: InvalidArgumentError "Cholesky decomposition was not
+ *     successful"), <0 = bad argument / CUDA error, text via gpb_last_error();
+ *   - work is enqueued on the handle's stream; calls that return host scalars synchronise that
+ *     stream before returning, the others are asynchronous;
+ *   - a handle is bound to one device and is not thread-safe; distinct handles are independent.
+ *   - hyper-parameters cross the boundary in CONSTRAINED space (variance, lengthscale, ...); the
+ *     softplus chain rule of gpflow.Parameter stays in the host layer.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_MAX_DIMS 16    /* input columns D the fused assembly supports */
+#define GPB_MAX_GROUPS 8   /* distinct distance computations per kernel expression */
+#define GPB_MAX_LEAVES 8   /* leaf kernels per expression */
+#define GPB_MAX_TERMS 8    /* products in the sum-of-products normal form */
+#define GPB_MAX_FACTORS 4  /* leaves per product */
+#define GPB_MAX_PARAMS 48  /* flat constrained hyper-parameter vector length */
+
+/* How a group reduces a pair (x, x') over its active dims to one scalar s. */
+enum gpb_group_kind {
+    GPB_GROUP_EUCLID = 0,       /* s = sum_d w_d (x_d - x'_d)^2      gpflow/utilities/ops.py square_distance */
+    GPB_GROUP_PERIODIC_SQ = 1,  /* s = sum_d w_d sin^2(pi (x_d - x'_d)/p)   gpflow/kernels/periodic.py, K_r2 bases */
+    GPB_GROUP_PERIODIC_ABS = 2, /* s = sum_d w_d |sin(pi (x_d - x'_d)/p)|   gpflow/kernels/periodic.py, K_r bases */
+    GPB_GROUP_DOT = 3           /* s = sum_d w_d x_d x'_d            gpflow/kernels/linears.py Linear */
+};
+
+/* gpflow/kernels/stationaries.py + linears.py leaf formulas. */
+enum gpb_leaf_kind {
+    GPB_LEAF_SE = 0,          /* variance * exp(-r2/2) */
+    GPB_LEAF_RQ = 1,          /* variance * (1 + r2/(2 alpha))^-alpha */
+    GPB_LEAF_MATERN12 = 2,    /* variance * exp(-r) */
+    GPB_LEAF_EXPONENTIAL = 3, /* variance * exp(-r/2) */
+    GPB_LEAF_MATERN32 = 4,
+    GPB_LEAF_MATERN52 = 5,
+    GPB_LEAF_LINEAR = 6       /* variance * s */
+};
+
+typedef struct {
+    int32_t kind;         /* gpb_group_kind */
+    uint32_t dim_mask;    /* bit d set <=> column d is active (GPflow active_dims) */
+    int32_t ard_index;    /* >=0: theta[ard_index + k] is the lengthscale of the k-th active dim (ARD); -1: isotropic */
+    int32_t period_index; /* periodic groups: theta index of the (scalar) period; else -1 */
+} gpb_group;
+
+typedef struct {
+    int32_t kind;        /* gpb_leaf_kind */
+    int32_t group;       /* index into groups[] */
+    int32_t var_index;   /* theta index of variance */
+    int32_t ls_index;    /* theta index of the scalar lengthscale; -1 for ARD (see group) and Linear */
+    int32_t alpha_index; /* RationalQuadratic alpha; else -1 */
+} gpb_leaf;
+
+typedef struct {
+    int32_t n_factors;
+    int32_t leaf[GPB_MAX_FACTORS];
+} gpb_term;
+
+/* Kernel expression in sum-of-products normal form: K = sum_t prod_f leaf[t][f].
+ * Replaces gpflow.kernels.{Sum,Product} trees built at GPR/main.py:105-114 and
+ * Multi-Input_GPR/main.py:126-135 (k1(active_dims) * k2(active_dims)). */
+typedef struct {
+    int32_t n_dims;   /* D of the X this expression is applied to */
+    int32_t n_params; /* length of the flat constrained theta vector */
+    int32_t n_groups, n_leaves, n_terms;
+    gpb_group groups[GPB_MAX_GROUPS];
+    gpb_leaf leaves[GPB_MAX_LEAVES];
+    gpb_term terms[GPB_MAX_TERMS];
+} gpb_kernel_spec;
+
+typedef struct gpb_handle gpb_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int gpb_create(gpb_handle** out, int device);
+int gpb_destroy(gpb_handle* h);
+const char* gpb_last_error(gpb_handle* h);
+/* cuda_stream is a cudaStream_t (NULL = legacy default stream).  Lets the torch host layer order
+ * engine work against its own allocations. */
+int gpb_set_stream(gpb_handle* h, void* cuda_stream);
+/* ABI version and build info ("sm_100a ..."); */
+int gpb_version(void);
+/* Number of engine kernels launched through this handle since creation (bench.py gpu_launches). */
+int64_t gpb_launch_count(gpb_handle* h);
+
+/* ---- kernel expression ---------------------------------------------------------------------- */
+/* Replaces the kernel object handed to gpflow.models.GPR(kernel=...) (GPR/model_trainer.py:15). */
+int gpb_set_kernel(gpb_handle* h, const gpb_kernel_spec* spec);
+
+/* ---- fused kernel-matrix assembly (north_star subsystem 1) --------------------------------------
+ * Replaces gpflow Kernel.__call__ -> K / K_diag (+ GPR._add_noise_cov, Kuu jitter) i.e. TF MatMul +
+ * Exp/Sqrt/Sin + AddN/Mul + set_diag, for GPR/model_trainer.py:15-20 and GPR/predictor.py:6.
+ * mode: 0 = full [N,N2] (d_X2 may differ from d_X); 1 = lower triangle of K(X,X) only (tiles on or
+ * below the diagonal; what the Cholesky consumes); 2 = K(X,X) computing lower tiles once and
+ * mirroring them (symmetric full).  diag_add is added to K[i][i] in modes 1,2 (noise / jitter). */
+int gpb_assemble(gpb_handle* h, const double* h_theta, const double* d_X, int64_t N, const double* d_X2,
+                 int64_t N2, int D, double* d_K, int64_t ldk, int mode, double diag_add);
+int gpb_kdiag(gpb_handle* h, const double* h_theta, const double* d_X, int64_t N, int D, double* d_out);
+
+/* ---- dense fp64 building blocks (north_star subsystem 2), exposed for tests / reuse ------------
+ * Replace tf.linalg.cholesky / tf.linalg.triangular_solve / tf.matmul. */
+/* In-place lower Cholesky of the row-major lower triangle of d_A [N,N] (tf.linalg.cholesky).  The
+ * strict upper triangle is workspace: zero inside 128-aligned diagonal blocks, unspecified elsewhere. */
+int gpb_potrf(gpb_handle* h, double* d_A, int64_t N, int64_t lda);
+/* As gpb_potrf, and additionally d_W (lower) = L^-1 (what tf.linalg.triangular_solve(L, .) applies). */
+int gpb_potrf_inv(gpb_handle* h, double* d_A, int64_t N, int64_t lda, double* d_W, int64_t ldw);
+/* d_Out (lower tiles) = d_W^T d_W, i.e. (L L^T)^-1 when d_W = L^-1 from gpb_potrf_inv. */
+int gpb_lauum(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo);
+/* C = alpha * op(A) op(B) + beta * C (tf.matmul); transa/transb: 0 = as stored, 1 = transposed.
+ * Row-major.  tri: 0 = full C, 1 = only tiles of C on/below the diagonal are computed (SYRK-style). */
+int gpb_gemm(gpb_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
+             const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C,
+             int64_t ldc, int tri);
+
+/* ---- exact GP regression (north_star subsystems 2-3) --------------------------------------------
+ * Replaces gpflow.models.GPR((X, Y), kernel, noise_variance) at GPR/model_trainer.py:15,
+ * Multi-Input_GPR/main.py:421-423, models/model_trainer.py:31.  d_X [N,D] row-major (ld = D),
+ * d_Yc [N] = Y - mean_function(X) (R = 1 on every reference call site).  Buffers are borrowed until
+ * the next set_data / destroy. */
+int gpb_gpr_set_data(gpb_handle* h, const double* d_X, int64_t N, int D, const double* d_Yc);
+/* log marginal likelihood: GPR.log_marginal_likelihood (gpflow/models/gpr.py) =
+ * -1/2 |L^-1 y|^2 - N/2 log 2pi - sum log L_ii, with L = chol(K + noise I). */
+int gpb_gpr_lml(gpb_handle* h, const double* h_theta, double noise_variance, double* h_lml);
+/* LML and d LML / d theta (constrained, n_params entries) and d LML / d noise_variance, via
+ * 1/2 tr((a a^T - K^-1) dK/dtheta) with dK/dtheta recomputed on the fly -- replaces the
+ * tf.GradientTape pass inside gpflow.optimizers.Scipy.minimize (GPR/model_trainer.py:18-19). */
+int gpb_gpr_lml_grad(gpb_handle* h, const double* h_theta, double noise_variance, double* h_lml,
+                     double* h_grad_theta, double* h_grad_noise);
+/* GPR.predict_f(Xnew, full_cov=False) (gpflow/posteriors.py GPRPosterior, conditionals/util.py
+ * base_conditional_with_lm), GPR/predictor.py:6, Multi-Input_GPR/main.py:434.
+ * d_mean, d_var: [Ns] device outputs (mean excludes mean_function(Xnew)). */
+int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Xs,
+                      int64_t Ns, double* d_mean, double* d_var);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

@@ -1,0 +1,206 @@
+"""ctypes binding of libgpb200.so (include/gpb200.h).  The only bridge between the Python host
+layer and the sm_100a engine: plain pointers and sizes, no torch types in any signature.
+
+There is no CPU fallback: if the library is missing or no B200 is visible, construction of an
+:class:`Engine` raises.  Importing this module never touches CUDA (so that the host-side logic
+and the ABI checks can be tested on a CPU-only box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgpb200.so")
+
+GPB_MAX_DIMS = 16
+GPB_MAX_GROUPS = 8
+GPB_MAX_LEAVES = 8
+GPB_MAX_TERMS = 8
+GPB_MAX_FACTORS = 4
+GPB_MAX_PARAMS = 48
+
+GROUP_EUCLID, GROUP_PERIODIC_SQ, GROUP_PERIODIC_ABS, GROUP_DOT = 0, 1, 2, 3
+LEAF_SE, LEAF_RQ, LEAF_MATERN12, LEAF_EXPONENTIAL, LEAF_MATERN32, LEAF_MATERN52, LEAF_LINEAR = range(7)
+
+
+class GpbGroup(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dim_mask", C.c_uint32), ("ard_index", C.c_int32), ("period_index", C.c_int32)]
+
+
+class GpbLeaf(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("group", C.c_int32), ("var_index", C.c_int32), ("ls_index", C.c_int32),
+                ("alpha_index", C.c_int32)]
+
+
+class GpbTerm(C.Structure):
+    _fields_ = [("n_factors", C.c_int32), ("leaf", C.c_int32 * GPB_MAX_FACTORS)]
+
+
+class GpbKernelSpec(C.Structure):
+    _fields_ = [("n_dims", C.c_int32), ("n_params", C.c_int32), ("n_groups", C.c_int32), ("n_leaves", C.c_int32),
+                ("n_terms", C.c_int32), ("groups", GpbGroup * GPB_MAX_GROUPS), ("leaves", GpbLeaf * GPB_MAX_LEAVES),
+                ("terms", GpbTerm * GPB_MAX_TERMS)]
+
+
+class CholeskyError(ValueError):
+    """Raised where GPflow/TF raise InvalidArgumentError('Cholesky decomposition was not
+    successful'): the covariance matrix is not positive definite at the current hyper-parameters."""
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+_P = C.c_void_p
+_D = C.c_double
+_I64 = C.c_int64
+_INT = C.c_int
+_DP = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); must list every symbol include/gpb200.h declares
+SIGNATURES = {
+    "gpb_version": (_INT, []),
+    "gpb_create": (_INT, [C.POINTER(_P), _INT]),
+    "gpb_destroy": (_INT, [_P]),
+    "gpb_last_error": (C.c_char_p, [_P]),
+    "gpb_set_stream": (_INT, [_P, _P]),
+    "gpb_launch_count": (_I64, [_P]),
+    "gpb_set_kernel": (_INT, [_P, C.POINTER(GpbKernelSpec)]),
+    "gpb_assemble": (_INT, [_P, _DP, _P, _I64, _P, _I64, _INT, _P, _I64, _INT, _D]),
+    "gpb_kdiag": (_INT, [_P, _DP, _P, _I64, _INT, _P]),
+    "gpb_potrf": (_INT, [_P, _P, _I64, _I64]),
+    "gpb_potrf_inv": (_INT, [_P, _P, _I64, _I64, _P, _I64]),
+    "gpb_lauum": (_INT, [_P, _P, _I64, _I64, _P, _I64]),
+    "gpb_gemm": (_INT, [_P, _INT, _INT, _I64, _I64, _I64, _D, _P, _I64, _P, _I64, _D, _P, _I64, _INT]),
+    "gpb_gpr_set_data": (_INT, [_P, _P, _I64, _INT, _P]),
+    "gpb_gpr_lml": (_INT, [_P, _DP, _D, _DP]),
+    "gpb_gpr_lml_grad": (_INT, [_P, _DP, _D, _DP, _DP, _DP]),
+    "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
+}
+
+
+def load_library() -> C.CDLL:
+    """dlopen libgpb200.so and declare every entry point.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} is missing: build it with `python -m portfoliooptgp_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback on this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _as_dp(a: np.ndarray):
+    return a.ctypes.data_as(_DP)
+
+
+class Engine:
+    """One gpb_handle bound to one CUDA device.  Device buffers are passed as integer addresses
+    (``tensor.data_ptr()``); ownership stays with the caller."""
+
+    def __init__(self, device: int = 0):
+        self._h = _P()
+        self._lib = load_library()
+        rc = self._lib.gpb_create(C.byref(self._h), int(device))
+        if rc != 0:
+            self._h = _P()
+            reasons = {-10: "no CUDA device visible", -13: "device is not sm_100 (B200) class", -2: "bad device index"}
+            raise EngineError(f"gpb_create failed ({rc}): {reasons.get(rc, 'CUDA initialisation error')}; "
+                              "the engine has no CPU fallback")
+        self.device = int(device)
+        self._spec_token = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.gpb_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc == 0:
+            return
+        msg = self._lib.gpb_last_error(self._h)
+        msg = msg.decode() if msg else ""
+        if rc > 0:
+            raise CholeskyError(f"{what}: {msg}")
+        raise EngineError(f"{what} failed ({rc}): {msg}")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.gpb_set_stream(self._h, _P(cuda_stream)), "gpb_set_stream")
+
+    def launch_count(self) -> int:
+        return int(self._lib.gpb_launch_count(self._h))
+
+    def set_kernel(self, spec: GpbKernelSpec, token=None):
+        if token is not None and token == self._spec_token:
+            return
+        self._check(self._lib.gpb_set_kernel(self._h, C.byref(spec)), "gpb_set_kernel")
+        self._spec_token = token
+
+    # -- assembly ----------------------------------------------------------------------------
+    def assemble(self, theta: np.ndarray, dX: int, N: int, dX2: Optional[int], N2: int, D: int, dK: int, ldk: int,
+                 mode: int, diag_add: float):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb_assemble(self._h, _as_dp(theta), _P(dX), N, _P(dX2) if dX2 else None, N2, D, _P(dK),
+                                           ldk, mode, float(diag_add)), "gpb_assemble")
+
+    def kdiag(self, theta: np.ndarray, dX: int, N: int, D: int, dout: int):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb_kdiag(self._h, _as_dp(theta), _P(dX), N, D, _P(dout)), "gpb_kdiag")
+
+    # -- dense --------------------------------------------------------------------------------
+    def potrf(self, dA: int, N: int, lda: int):
+        self._check(self._lib.gpb_potrf(self._h, _P(dA), N, lda), "gpb_potrf")
+
+    def potrf_inv(self, dA: int, N: int, lda: int, dW: int, ldw: int):
+        self._check(self._lib.gpb_potrf_inv(self._h, _P(dA), N, lda, _P(dW), ldw), "gpb_potrf_inv")
+
+    def lauum(self, dW: int, N: int, ldw: int, dOut: int, ldo: int):
+        self._check(self._lib.gpb_lauum(self._h, _P(dW), N, ldw, _P(dOut), ldo), "gpb_lauum")
+
+    def gemm(self, transa, transb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, tri=0):
+        self._check(self._lib.gpb_gemm(self._h, int(transa), int(transb), M, N, K, float(alpha), _P(dA), lda, _P(dB),
+                                       ldb, float(beta), _P(dC), ldc, int(tri)), "gpb_gemm")
+
+    # -- exact GP -----------------------------------------------------------------------------
+    def gpr_set_data(self, dX: int, N: int, D: int, dYc: int):
+        self._check(self._lib.gpb_gpr_set_data(self._h, _P(dX), N, D, _P(dYc)), "gpb_gpr_set_data")
+
+    def gpr_lml(self, theta: np.ndarray, noise: float) -> float:
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = C.c_double()
+        self._check(self._lib.gpb_gpr_lml(self._h, _as_dp(theta), float(noise), C.byref(out)), "gpb_gpr_lml")
+        return out.value
+
+    def gpr_lml_grad(self, theta: np.ndarray, noise: float):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        lml = C.c_double()
+        gnoise = C.c_double()
+        g = np.zeros(theta.size, dtype=np.float64)
+        self._check(self._lib.gpb_gpr_lml_grad(self._h, _as_dp(theta), float(noise), C.byref(lml), _as_dp(g),
+                                               C.byref(gnoise)), "gpb_gpr_lml_grad")
+        return lml.value, g, gnoise.value
+
+    def gpr_predict_f(self, theta: np.ndarray, noise: float, dXs: int, Ns: int, dmean: int, dvar: int):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb_gpr_predict_f(self._h, _as_dp(theta), float(noise), _P(dXs), Ns, _P(dmean), _P(dvar)),
+                    "gpb_gpr_predict_f")

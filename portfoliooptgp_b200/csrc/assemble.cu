@@ -1,0 +1,290 @@
+// assemble.cu -- fused kernel-matrix assembly and the fused gradient reduction (north_star
+// subsystems 1 and 3).
+//
+// Replaces, in one pass over the output, what GPflow issues as separate TF ops for
+// kernel(X) / kernel(X, X2) / K_diag + GPR._add_noise_cov:
+// MatMul + broadcasts for the distances, Exp/Sqrt/Sin per leaf, AddN/Mul for Sum/Product and
+// set_diag for the noise.  No intermediate [N,N] (or Periodic's [N,N,D]) tensor exists here:
+// the X tiles are staged in shared memory, every leaf is evaluated in registers, and the finished
+// tile is written once with 16-byte stores.
+//
+// HBM roofline: algorithmic bytes = 8*N*N2 (full) or 8*N(N+1)/2 (lower) written + 8*D*(N+N2) read.
+#include "engine.cuh"
+
+namespace gpb {
+
+constexpr int TILE = 64;       // output tile edge
+constexpr int ROWS_PT = 8;     // rows per thread
+constexpr int ASM_THREADS = 256;
+
+__device__ __forceinline__ void tri_tile_index(int64_t b, int& ti, int& tj) {
+    // b = ti (ti + 1) / 2 + tj, 0 <= tj <= ti
+    int t = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(t + 1) * (t + 2) / 2 <= b) ++t;
+    while ((int64_t)t * (t + 1) / 2 > b) --t;
+    ti = t;
+    tj = (int)(b - (int64_t)t * (t + 1) / 2);
+}
+
+// mode 0: full cross K(X, X2); 1: lower tiles of K(X, X) (+diag_add); 2: lower tiles + mirrored copy.
+template <int DP>
+__global__ void __launch_bounds__(ASM_THREADS)
+assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
+                const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
+                double diag_add, int tiles_n) {
+    __shared__ double xs_i[TILE][DP];
+    __shared__ double xs_j[TILE][DP];
+    __shared__ double stage[TILE * TILE];  // mirror staging (mode 2), rotation-swizzled columns
+
+    int ti, tj;
+    if (mode == 0) {
+        ti = blockIdx.x / tiles_n;
+        tj = blockIdx.x % tiles_n;
+    } else {
+        tri_tile_index(blockIdx.x, ti, tj);
+    }
+    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    const int tid = threadIdx.x;
+
+    // stage the two X tiles (zero-padded to DP columns, rows beyond N zero)
+    for (int e = tid; e < TILE * DP; e += ASM_THREADS) {
+        int r = e / DP, d = e % DP;
+        int64_t gi = row0 + r, gj = col0 + r;
+        xs_i[r][d] = (gi < N && d < D) ? X[gi * D + d] : 0.0;
+        xs_j[r][d] = (gj < N2 && d < D) ? X2[gj * D + d] : 0.0;
+    }
+    __syncthreads();
+
+    const int tx = tid & 31, ty = tid >> 5;
+    const int c0 = 2 * tx;
+    double xj0[DP], xj1[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        xj0[d] = xs_j[c0][d];
+        xj1[d] = xs_j[c0 + 1][d];
+    }
+    const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(Kout) & 15) == 0);
+    const bool diag_tile = (mode != 0) && (ti == tj);
+
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS_PT; ++rr) {
+        const int r = ty * ROWS_PT + rr;
+        const int64_t gi = row0 + r;
+        double xi[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) xi[d] = xs_i[r][d];
+        double v0 = kernel_value<DP>(kp, xi, xj0);
+        double v1 = kernel_value<DP>(kp, xi, xj1);
+        if (diag_tile) {
+            if (r == c0) v0 += diag_add;
+            if (r == c0 + 1) v1 += diag_add;
+        }
+        if (mode == 2) {
+            stage[r * TILE + ((c0 + r) & (TILE - 1))] = v0;
+            stage[r * TILE + ((c0 + 1 + r) & (TILE - 1))] = v1;
+        }
+        if (gi < N) {
+            const int64_t gj = col0 + c0;
+            double* p = Kout + gi * ldk + gj;
+            if (vec_ok && gj + 1 < N2) {
+                *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+            } else {
+                if (gj < N2) p[0] = v0;
+                if (gj + 1 < N2) p[1] = v1;
+            }
+        }
+    }
+    if (mode == 2 && ti != tj) {
+        __syncthreads();
+        // transposed tile: out[col0 + r][row0 + c] = stage[c][r]
+#pragma unroll 1
+        for (int rr = 0; rr < ROWS_PT; ++rr) {
+            const int r = ty * ROWS_PT + rr;
+            const int64_t gi = col0 + r;
+            if (gi < N) {
+                const int64_t gj = row0 + c0;
+                double v0 = stage[c0 * TILE + ((r + c0) & (TILE - 1))];
+                double v1 = stage[(c0 + 1) * TILE + ((r + c0 + 1) & (TILE - 1))];
+                double* p = Kout + gi * ldk + gj;
+                if (vec_ok && gj + 1 < N) {
+                    *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+                } else {
+                    if (gj < N) p[0] = v0;
+                    if (gj + 1 < N) p[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+template <int DP>
+__global__ void kdiag_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N, int D,
+                             double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double xi[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) xi[d] = (d < D) ? X[i * D + d] : 0.0;
+    out[i] = kernel_diag_value<DP>(kp, xi);
+}
+
+// ---- fused gradient reduction ----------------------------------------------------------------------
+// partial[b][p] = sum over the tile of c_ij (alpha_i alpha_j - Kinv_ij) dK_ij/dtheta_p, p < P;
+// partial[b][P] = sum over diagonal elements of (alpha_i^2 - Kinv_ii).   dK/dtheta is recomputed from
+// the X tiles and never written.  HBM bytes: one read of the lower triangle of
+// Kinv (8 N(N+1)/2).
+template <int DP>
+__global__ void __launch_bounds__(ASM_THREADS)
+grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N, int D,
+                   const double* __restrict__ Kinv, int64_t ldk, const double* __restrict__ alpha,
+                   double* __restrict__ partial) {
+    __shared__ double xs_i[TILE][DP];
+    __shared__ double xs_j[TILE][DP];
+    __shared__ double al_i[TILE], al_j[TILE];
+    __shared__ double red[ASM_THREADS / 32][GPB_MAX_PARAMS + 1];
+
+    int ti, tj;
+    tri_tile_index(blockIdx.x, ti, tj);
+    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < TILE * DP; e += ASM_THREADS) {
+        int r = e / DP, d = e % DP;
+        int64_t gi = row0 + r, gj = col0 + r;
+        xs_i[r][d] = (gi < N && d < D) ? X[gi * D + d] : 0.0;
+        xs_j[r][d] = (gj < N && d < D) ? X[gj * D + d] : 0.0;
+    }
+    if (tid < TILE) {
+        al_i[tid] = (row0 + tid < N) ? alpha[row0 + tid] : 0.0;
+        al_j[tid] = (col0 + tid < N) ? alpha[col0 + tid] : 0.0;
+    }
+    __syncthreads();
+
+    const int P = kp.n_params;
+    double acc[GPB_MAX_PARAMS + 1];
+    for (int p = 0; p <= P; ++p) acc[p] = 0.0;
+
+    const int tx = tid & 31, ty = tid >> 5;
+    const int c0 = 2 * tx;
+    double xj0[DP], xj1[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+        xj0[d] = xs_j[c0][d];
+        xj1[d] = xs_j[c0 + 1][d];
+    }
+    const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(Kinv) & 15) == 0);
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS_PT; ++rr) {
+        const int r = ty * ROWS_PT + rr;
+        const int64_t gi = row0 + r;
+        if (gi >= N) continue;
+        const int64_t gj = col0 + c0;
+        if (gj > gi) continue;  // strictly above the diagonal: both columns skipped
+        double k0 = 0.0, k1 = 0.0;
+        const double* p = Kinv + gi * ldk + gj;
+        if (vec_ok && gj + 1 <= gi) {
+            double2 t = *reinterpret_cast<const double2*>(p);
+            k0 = t.x; k1 = t.y;
+        } else {
+            k0 = p[0];
+            if (gj + 1 <= gi) k1 = p[1];
+        }
+        double xi[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) xi[d] = xs_i[r][d];
+        const double ai = al_i[r];
+        {
+            double w = ai * al_j[c0] - k0;
+            if (gj == gi) { acc[P] += w; } else { w *= 2.0; }
+            kernel_value_grad<DP>(kp, xi, xj0, w, acc);
+        }
+        if (gj + 1 <= gi) {
+            double w = ai * al_j[c0 + 1] - k1;
+            if (gj + 1 == gi) { acc[P] += w; } else { w *= 2.0; }
+            kernel_value_grad<DP>(kp, xi, xj1, w, acc);
+        }
+    }
+    // block reduction in a fixed order (deterministic): warp shuffle, then warp 0 sums the 8 rows
+    for (int p = 0; p <= P; ++p) {
+        double v = acc[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (tx == 0) red[ty][p] = v;
+    }
+    __syncthreads();
+    if (tid <= P) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ASM_THREADS / 32; ++w) v += red[w][tid];
+        partial[(int64_t)blockIdx.x * (GPB_MAX_PARAMS + 1) + tid] = v;
+    }
+}
+
+// out[p] = sum_b partial[b][p] in a fixed order (one block per p, tree inside the block).
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int64_t nblocks, int stride, double* out) {
+    __shared__ double sm[256];
+    const int p = blockIdx.x;
+    double v = 0.0;
+    for (int64_t b = threadIdx.x; b < nblocks; b += 256) v += partial[b * stride + p];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[p] = sm[0];
+}
+
+static inline int pad_dims(int D) {
+    int dp = 1;
+    while (dp < D) dp <<= 1;
+    return dp;
+}
+
+#define GPB_DISPATCH_DP(D, CALL)                                   \
+    switch (pad_dims(D)) {                                         \
+        case 1: { constexpr int DP = 1; CALL; } break;             \
+        case 2: { constexpr int DP = 2; CALL; } break;             \
+        case 4: { constexpr int DP = 4; CALL; } break;             \
+        case 8: { constexpr int DP = 8; CALL; } break;             \
+        default: { constexpr int DP = 16; CALL; } break;           \
+    }
+
+int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, const double* d_X2, int64_t N2,
+                    int D, double* d_K, int64_t ldk, int mode, double diag_add) {
+    if (N <= 0 || N2 <= 0) return 0;
+    if (D < 1 || D > GPB_MAX_DIMS) return set_error(h, -2, "assemble: D=%d outside [1,%d]", D, GPB_MAX_DIMS);
+    if (mode != 0 && (d_X2 != d_X || N2 != N)) return set_error(h, -2, "assemble: symmetric modes need X2 == X");
+    const int tiles_m = (int)((N + TILE - 1) / TILE), tiles_n = (int)((N2 + TILE - 1) / TILE);
+    const int64_t nblk = (mode == 0) ? (int64_t)tiles_m * tiles_n : (int64_t)tiles_m * (tiles_m + 1) / 2;
+    if (nblk > 0x7fffffffLL) return set_error(h, -2, "assemble: too many tiles");
+    GPB_DISPATCH_DP(D, (assemble_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(
+                           kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n)));
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "assemble_kernel launch");
+}
+
+int launch_kdiag(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, int D, double* d_out) {
+    if (N <= 0) return 0;
+    if (D < 1 || D > GPB_MAX_DIMS) return set_error(h, -2, "kdiag: D=%d outside [1,%d]", D, GPB_MAX_DIMS);
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    GPB_DISPATCH_DP(D, (kdiag_kernel<DP><<<blocks, 256, 0, h->stream>>>(kp, d_X, N, D, d_out)));
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "kdiag_kernel launch");
+}
+
+int launch_grad_reduce(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, int D, const double* d_Kinv,
+                       int64_t ldk, const double* d_alpha, double* d_out) {
+    const int tiles = (int)((N + TILE - 1) / TILE);
+    const int64_t nblk = (int64_t)tiles * (tiles + 1) / 2;
+    double* partial = workspace(h, BUF_RED, (size_t)nblk * (GPB_MAX_PARAMS + 1) * sizeof(double));
+    if (!partial) return -1;
+    GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv, ldk,
+                                                                                              d_alpha, partial)));
+    int rc = check_cuda(h, cudaGetLastError(), "grad_reduce_kernel launch");
+    if (rc) return rc;
+    reduce_partials_kernel<<<kp.n_params + 1, 256, 0, h->stream>>>(partial, nblk, GPB_MAX_PARAMS + 1, d_out);
+    h->launches += 2;
+    return check_cuda(h, cudaGetLastError(), "reduce_partials_kernel launch");
+}
+
+}  // namespace gpb

@@ -1,0 +1,347 @@
+// capi.cu -- the extern "C" surface of libgpb200.so (include/gpb200.h): handle lifecycle, error
+// reporting, workspace management, kernel-spec validation, and thin forwarding to the engine.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "engine.cuh"
+
+namespace gpb {
+
+int set_error(gpb_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+int check_cuda(gpb_handle* h, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return set_error(h, -100 - (int)e, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+double* workspace(gpb_handle* h, int id, size_t bytes) {
+    if (bytes <= h->buf_bytes[id] && h->buf[id]) return h->buf[id];
+    if (h->buf[id]) {
+        cudaFree(h->buf[id]);  // synchronises the device: no kernel can still be using the old block
+        h->buf[id] = nullptr;
+        h->buf_bytes[id] = 0;
+    }
+    // grow with head-room so that rolling-window refits (N, N+1, ...) do not reallocate every call
+    size_t want = bytes + bytes / 8 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        check_cuda(h, e, "workspace cudaMalloc");
+        return nullptr;
+    }
+    h->buf[id] = static_cast<double*>(p);
+    h->buf_bytes[id] = want;
+    return h->buf[id];
+}
+
+double* pinned(gpb_handle* h, size_t bytes) {
+    if (bytes <= h->h_pinned_bytes && h->h_pinned) return h->h_pinned;
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned = nullptr;
+    h->h_pinned_bytes = 0;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
+        check_cuda(h, e, "cudaMallocHost");
+        return nullptr;
+    }
+    h->h_pinned = static_cast<double*>(p);
+    h->h_pinned_bytes = bytes;
+    return h->h_pinned;
+}
+
+static int validate_spec(gpb_handle* h, const gpb_kernel_spec* s) {
+    if (s->n_dims < 1 || s->n_dims > GPB_MAX_DIMS) return set_error(h, -2, "kernel spec: n_dims=%d outside [1,%d]", s->n_dims, GPB_MAX_DIMS);
+    if (s->n_params < 1 || s->n_params > GPB_MAX_PARAMS) return set_error(h, -2, "kernel spec: n_params=%d outside [1,%d]", s->n_params, GPB_MAX_PARAMS);
+    if (s->n_groups < 1 || s->n_groups > GPB_MAX_GROUPS) return set_error(h, -2, "kernel spec: n_groups=%d outside [1,%d]", s->n_groups, GPB_MAX_GROUPS);
+    if (s->n_leaves < 1 || s->n_leaves > GPB_MAX_LEAVES) return set_error(h, -2, "kernel spec: n_leaves=%d outside [1,%d]", s->n_leaves, GPB_MAX_LEAVES);
+    if (s->n_terms < 1 || s->n_terms > GPB_MAX_TERMS) return set_error(h, -2, "kernel spec: n_terms=%d outside [1,%d]", s->n_terms, GPB_MAX_TERMS);
+    auto idx_ok = [&](int i) { return i >= 0 && i < s->n_params; };
+    for (int g = 0; g < s->n_groups; ++g) {
+        const gpb_group& G = s->groups[g];
+        if (G.kind < 0 || G.kind > GPB_GROUP_DOT) return set_error(h, -2, "kernel spec: group %d bad kind %d", g, G.kind);
+        if (G.dim_mask == 0 || (s->n_dims < 32 && (G.dim_mask >> s->n_dims) != 0))
+            return set_error(h, -2, "kernel spec: group %d dim_mask 0x%x invalid for D=%d", g, G.dim_mask, s->n_dims);
+        const int nact = __builtin_popcount(G.dim_mask);
+        if (G.ard_index >= 0 && (!idx_ok(G.ard_index) || !idx_ok(G.ard_index + nact - 1)))
+            return set_error(h, -2, "kernel spec: group %d ARD index out of range", g);
+        const bool per = (G.kind == GPB_GROUP_PERIODIC_SQ || G.kind == GPB_GROUP_PERIODIC_ABS);
+        if (per != (G.period_index >= 0)) return set_error(h, -2, "kernel spec: group %d period index inconsistent", g);
+        if (per && !idx_ok(G.period_index)) return set_error(h, -2, "kernel spec: group %d period index out of range", g);
+    }
+    for (int l = 0; l < s->n_leaves; ++l) {
+        const gpb_leaf& L = s->leaves[l];
+        if (L.kind < 0 || L.kind > GPB_LEAF_LINEAR) return set_error(h, -2, "kernel spec: leaf %d bad kind %d", l, L.kind);
+        if (L.group < 0 || L.group >= s->n_groups) return set_error(h, -2, "kernel spec: leaf %d bad group", l);
+        if (!idx_ok(L.var_index)) return set_error(h, -2, "kernel spec: leaf %d variance index out of range", l);
+        const gpb_group& G = s->groups[L.group];
+        if (L.kind == GPB_LEAF_LINEAR) {
+            if (G.kind != GPB_GROUP_DOT || L.ls_index >= 0) return set_error(h, -2, "kernel spec: Linear leaf %d needs a DOT group and no lengthscale", l);
+        } else {
+            if (G.kind == GPB_GROUP_DOT) return set_error(h, -2, "kernel spec: stationary leaf %d on a DOT group", l);
+            if ((L.ls_index >= 0) == (G.ard_index >= 0)) return set_error(h, -2, "kernel spec: leaf %d needs exactly one of scalar/ARD lengthscale", l);
+            if (L.ls_index >= 0 && !idx_ok(L.ls_index)) return set_error(h, -2, "kernel spec: leaf %d lengthscale index out of range", l);
+            const bool r_kind = (L.kind >= GPB_LEAF_MATERN12 && L.kind <= GPB_LEAF_MATERN52);
+            if (G.kind == GPB_GROUP_PERIODIC_ABS && !r_kind) return set_error(h, -2, "kernel spec: leaf %d: PERIODIC_ABS feeds K_r kernels only", l);
+            if (G.kind == GPB_GROUP_PERIODIC_SQ && r_kind) return set_error(h, -2, "kernel spec: leaf %d: K_r kernels need PERIODIC_ABS", l);
+        }
+        if ((L.kind == GPB_LEAF_RQ) != (L.alpha_index >= 0)) return set_error(h, -2, "kernel spec: leaf %d alpha index inconsistent", l);
+        if (L.alpha_index >= 0 && !idx_ok(L.alpha_index)) return set_error(h, -2, "kernel spec: leaf %d alpha index out of range", l);
+    }
+    for (int t = 0; t < s->n_terms; ++t) {
+        const gpb_term& T = s->terms[t];
+        if (T.n_factors < 1 || T.n_factors > GPB_MAX_FACTORS) return set_error(h, -2, "kernel spec: term %d has %d factors", t, T.n_factors);
+        for (int f = 0; f < T.n_factors; ++f)
+            if (T.leaf[f] < 0 || T.leaf[f] >= s->n_leaves) return set_error(h, -2, "kernel spec: term %d factor %d bad leaf", t, f);
+    }
+    return 0;
+}
+
+int build_dev_kernel(gpb_handle* h, const double* theta, DevKernel* out) {
+    if (!h->has_spec) return set_error(h, -3, "no kernel set (gpb_set_kernel)");
+    const gpb_kernel_spec& s = h->spec;
+    for (int p = 0; p < s.n_params; ++p)
+        if (!(theta[p] == theta[p])) return set_error(h, -2, "theta[%d] is NaN", p);
+    memset(out, 0, sizeof(DevKernel));
+    out->n_dims = s.n_dims; out->n_params = s.n_params;
+    out->n_groups = s.n_groups; out->n_leaves = s.n_leaves; out->n_terms = s.n_terms;
+    for (int g = 0; g < s.n_groups; ++g) {
+        const gpb_group& G = s.groups[g];
+        DevGroup& d = out->groups[g];
+        d.kind = G.kind; d.ard_index = G.ard_index; d.period_index = G.period_index;
+        d.inv_period = (G.period_index >= 0) ? 1.0 / theta[G.period_index] : 0.0;
+        int k = 0;
+        for (int dim = 0; dim < GPB_MAX_DIMS; ++dim) {
+            d.w[dim] = 0.0; d.inv_ls[dim] = 0.0; d.ard_slot[dim] = 0;
+            if (dim < s.n_dims && ((G.dim_mask >> dim) & 1u)) {
+                if (G.ard_index >= 0) {
+                    const double l = theta[G.ard_index + k];
+                    if (!(l > 0.0)) return set_error(h, -2, "ARD lengthscale theta[%d]=%g must be > 0", G.ard_index + k, l);
+                    d.w[dim] = (G.kind == GPB_GROUP_PERIODIC_ABS) ? 1.0 / l : 1.0 / (l * l);
+                    d.inv_ls[dim] = 1.0 / l;
+                    d.ard_slot[dim] = k;
+                } else {
+                    d.w[dim] = 1.0;
+                }
+                ++k;
+            }
+        }
+    }
+    for (int l = 0; l < s.n_leaves; ++l) {
+        const gpb_leaf& L = s.leaves[l];
+        DevLeaf& d = out->leaves[l];
+        d.kind = L.kind; d.group = L.group;
+        d.var_index = L.var_index; d.ls_index = L.ls_index; d.alpha_index = L.alpha_index;
+        d.arg_is_r = (s.groups[L.group].kind == GPB_GROUP_PERIODIC_ABS) ? 1 : 0;
+        d.variance = theta[L.var_index];
+        d.alpha = (L.alpha_index >= 0) ? theta[L.alpha_index] : 1.0;
+        if (L.ls_index >= 0) {
+            const double ls = theta[L.ls_index];
+            if (!(ls > 0.0)) return set_error(h, -2, "lengthscale theta[%d]=%g must be > 0", L.ls_index, ls);
+            d.inv_ls = 1.0 / ls;
+            d.scale = d.arg_is_r ? 1.0 / ls : 1.0 / (ls * ls);
+        } else {
+            d.inv_ls = 0.0;
+            d.scale = 1.0;
+        }
+    }
+    for (int t = 0; t < s.n_terms; ++t) {
+        out->terms[t].n_factors = s.terms[t].n_factors;
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) out->terms[t].leaf[f] = s.terms[t].leaf[f];
+    }
+    return 0;
+}
+
+}  // namespace gpb
+
+using namespace gpb;
+
+#define GPB_ENTER(h)                          \
+    if (!(h)) return -1;                      \
+    {                                         \
+        cudaError_t e_ = cudaSetDevice((h)->device); \
+        if (e_ != cudaSuccess) return check_cuda((h), e_, "cudaSetDevice"); \
+    }
+
+extern "C" {
+
+int gpb_version(void) { return 100; }
+
+int gpb_create(gpb_handle** out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return -10;  // no CUDA device: there is no CPU fallback
+    if (device < 0 || device >= count) return -2;
+    if (cudaSetDevice(device) != cudaSuccess) return -11;
+    gpb_handle* h = new (std::nothrow) gpb_handle();
+    if (!h) return -12;
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        h->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            delete h;
+            return -13;  // built for sm_100a only
+        }
+    }
+    cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming);
+    *out = h;
+    return 0;
+}
+
+int gpb_destroy(gpb_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 8; ++i)
+        if (h->buf[i]) cudaFree(h->buf[i]);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    delete h;
+    return 0;
+}
+
+const char* gpb_last_error(gpb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gpb_set_stream(gpb_handle* h, void* cuda_stream) {
+    if (!h) return -1;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return 0;
+}
+
+int64_t gpb_launch_count(gpb_handle* h) { return h ? h->launches : -1; }
+
+int gpb_set_kernel(gpb_handle* h, const gpb_kernel_spec* spec) {
+    if (!h || !spec) return -1;
+    int rc = validate_spec(h, spec);
+    if (rc) return rc;
+    h->spec = *spec;
+    h->has_spec = true;
+    return 0;
+}
+
+int gpb_assemble(gpb_handle* h, const double* h_theta, const double* d_X, int64_t N, const double* d_X2, int64_t N2,
+                 int D, double* d_K, int64_t ldk, int mode, double diag_add) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_X || !d_K) return set_error(h, -2, "assemble: null pointer");
+    if (mode < 0 || mode > 2) return set_error(h, -2, "assemble: bad mode %d", mode);
+    if (!d_X2) { d_X2 = d_X; N2 = N; }
+    if (ldk < N2) return set_error(h, -2, "assemble: ldk < N2");
+    DevKernel kp;
+    int rc = build_dev_kernel(h, h_theta, &kp);
+    if (rc) return rc;
+    if (kp.n_dims != D) return set_error(h, -2, "assemble: kernel expects D=%d, got %d", kp.n_dims, D);
+    return launch_assemble(h, kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add);
+}
+
+int gpb_kdiag(gpb_handle* h, const double* h_theta, const double* d_X, int64_t N, int D, double* d_out) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_X || !d_out) return set_error(h, -2, "kdiag: null pointer");
+    DevKernel kp;
+    int rc = build_dev_kernel(h, h_theta, &kp);
+    if (rc) return rc;
+    if (kp.n_dims != D) return set_error(h, -2, "kdiag: kernel expects D=%d, got %d", kp.n_dims, D);
+    return launch_kdiag(h, kp, d_X, N, D, d_out);
+}
+
+static int potrf_common(gpb_handle* h, double* d_A, int64_t N, int64_t lda, double* d_W, int64_t ldw) {
+    if (!d_A || N <= 0 || lda < N) return set_error(h, -2, "potrf: bad arguments");
+    if (N > 0x7fffffff) return set_error(h, -2, "potrf: N too large");
+    const int64_t nblk = (N + 127) / 128;
+    double* v = workspace(h, BUF_DINV, (size_t)(nblk + 16) * sizeof(double));
+    if (!v) return -1;
+    int* info = reinterpret_cast<int*>(v + nblk);
+    int rc = factor_inv(h, d_A, lda, d_W, ldw, N, v, info, true);
+    if (rc) return rc;
+    double* hp = pinned(h, (size_t)(64 + 2) * sizeof(double));
+    if (!hp) return -1;
+    cudaError_t e = cudaMemcpyAsync(hp + 64, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "potrf sync");
+    const int inf = *reinterpret_cast<int*>(hp + 64);
+    if (inf > 0) set_error(h, inf, "Cholesky decomposition was not successful: non-positive pivot at row %d", inf);
+    return inf;
+}
+
+int gpb_potrf(gpb_handle* h, double* d_A, int64_t N, int64_t lda) {
+    GPB_ENTER(h);
+    const int64_t ldw = (N + 15) / 16 * 16;
+    double* W = workspace(h, BUF_W, (size_t)((N + 127) / 128 * 128) * ldw * sizeof(double));
+    if (!W) return -1;
+    return potrf_common(h, d_A, N, lda, W, ldw);
+}
+
+int gpb_potrf_inv(gpb_handle* h, double* d_A, int64_t N, int64_t lda, double* d_W, int64_t ldw) {
+    GPB_ENTER(h);
+    if (!d_W || ldw < N) return set_error(h, -2, "potrf_inv: bad W");
+    return potrf_common(h, d_A, N, lda, d_W, ldw);
+}
+
+int gpb_lauum(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo) {
+    GPB_ENTER(h);
+    if (!d_W || !d_Out || N <= 0 || ldw < N || ldo < N) return set_error(h, -2, "lauum: bad arguments");
+    return lauum_lower(h, d_W, N, ldw, d_Out, ldo);
+}
+
+int gpb_gemm(gpb_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha, const double* d_A,
+             int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C, int64_t ldc, int tri) {
+    GPB_ENTER(h);
+    if (!d_A || !d_B || !d_C) return set_error(h, -2, "gemm: null pointer");
+    GemmArgs g;
+    g.transa = transa; g.transb = transb; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+    g.A = d_A; g.lda = lda; g.B = d_B; g.ldb = ldb; g.C = d_C; g.ldc = ldc; g.tri = tri;
+    return launch_gemm(h, g, h->stream);
+}
+
+int gpb_gpr_set_data(gpb_handle* h, const double* d_X, int64_t N, int D, const double* d_Yc) {
+    if (!h) return -1;
+    if (!d_X || !d_Yc || N <= 0) return set_error(h, -2, "set_data: bad arguments");
+    if (D < 1 || D > GPB_MAX_DIMS) return set_error(h, -2, "set_data: D=%d outside [1,%d]", D, GPB_MAX_DIMS);
+    if (N > 0x7fffff00LL) return set_error(h, -2, "set_data: N too large");
+    h->d_X = d_X; h->d_Yc = d_Yc; h->N = N; h->D = D;
+    return 0;
+}
+
+int gpb_gpr_lml(gpb_handle* h, const double* h_theta, double noise_variance, double* h_lml) {
+    GPB_ENTER(h);
+    if (!h_theta || !h_lml) return set_error(h, -2, "gpr_lml: null pointer");
+    return gpr_lml(h, h_theta, noise_variance, h_lml, nullptr, nullptr, 0);
+}
+
+int gpb_gpr_lml_grad(gpb_handle* h, const double* h_theta, double noise_variance, double* h_lml, double* h_grad_theta,
+                     double* h_grad_noise) {
+    GPB_ENTER(h);
+    if (!h_theta || !h_lml || !h_grad_theta || !h_grad_noise) return set_error(h, -2, "gpr_lml_grad: null pointer");
+    return gpr_lml(h, h_theta, noise_variance, h_lml, h_grad_theta, h_grad_noise, 1);
+}
+
+int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Xs, int64_t Ns,
+                      double* d_mean, double* d_var) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "predict_f: null pointer");
+    return gpr_predict_f(h, h_theta, noise_variance, d_Xs, Ns, d_mean, d_var);
+}
+
+}  // extern "C"

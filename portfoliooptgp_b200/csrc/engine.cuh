@@ -1,0 +1,96 @@
+// engine.cuh -- internal C++ interface of libgpb200: the handle, workspace management and the
+// launch wrappers each .cu file provides to capi.cu.  Nothing here crosses the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "kernel_eval.cuh"
+
+struct gpb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // look-ahead panel work
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    bool has_spec = false;
+    gpb_kernel_spec spec;
+
+    // exact-GP binding
+    const double* d_X = nullptr;
+    const double* d_Yc = nullptr;
+    int64_t N = 0;
+    int D = 0;
+
+    // grow-only device workspaces
+    double* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t buf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double* h_pinned = nullptr;  // small pinned staging area for scalar results
+    size_t h_pinned_bytes = 0;
+};
+
+namespace gpb {
+
+enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7 };
+
+int set_error(gpb_handle* h, int code, const char* fmt, ...);
+int check_cuda(gpb_handle* h, cudaError_t e, const char* what);
+// returns nullptr (and sets error) on failure
+double* workspace(gpb_handle* h, int id, size_t bytes);
+double* pinned(gpb_handle* h, size_t bytes);
+
+// spec + theta -> device descriptor (host side, validates ranges)
+int build_dev_kernel(gpb_handle* h, const double* theta, DevKernel* out);
+
+// ---- assemble.cu
+int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, const double* d_X2, int64_t N2,
+                    int D, double* d_K, int64_t ldk, int mode, double diag_add);
+int launch_kdiag(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, int D, double* d_out);
+// grad reduction: out[p] = sum_{i>=j} c_ij W_ij dK_ij/dtheta_p with W = alpha alpha^T - Kinv (lower stored),
+// c_ij = 1 (i == j) or 2 (i > j); also out[n_params] = trace(W) (noise gradient, before the 1/2).
+int launch_grad_reduce(gpb_handle* h, const DevKernel& kp, const double* d_X, int64_t N, int D, const double* d_Kinv,
+                       int64_t ldk, const double* d_alpha, double* d_out /* n_params + 1, zeroed here */);
+
+// ---- dgemm.cu
+// C[M,N] = alpha * op(A) op(B) + beta * C (row-major).  tri: 1 = only tiles with row-block >= col-block.
+// k_limit_tri: 0 none; 1 = A is lower-triangular [M,K] (skip k-blocks beyond the row block); see dgemm.cu.
+struct GemmArgs {
+    int transa = 0, transb = 0;
+    int64_t M = 0, N = 0, K = 0;
+    double alpha = 1.0, beta = 0.0;
+    const double* A = nullptr; int64_t lda = 0;
+    const double* B = nullptr; int64_t ldb = 0;
+    double* C = nullptr; int64_t ldc = 0;
+    int tri = 0;         // 1: compute only lower tiles of C (square M == N)
+    int a_lower = 0;     // 1: op(A) [M,K] is lower triangular, K == M: k-range of row block i limited to <= i
+    int a_upper = 0;     // 1: op(A) [M,K] is upper triangular, K == M: k-range starts at the row block
+    int b_lower = 0;     // 1: op(B) [K,N] is lower triangular, K == N: k-range starts at the col block
+    int b_upper = 0;     // 1: op(B) [K,N] is upper triangular: k-range ends at the col block
+};
+int launch_gemm(gpb_handle* h, const GemmArgs& a, cudaStream_t stream);
+
+// ---- cholesky.cu
+// A (lower, in place) -> L on the diagonal blocks (and everywhere when keepL), W = L^-1 (lower, zero
+// strict-upper inside 128-aligned diagonal blocks), logdiag[b] = sum of log L_ii over block b,
+// *d_info = 1-based index of the first non-positive pivot (0 = ok).
+int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag, int* d_info,
+               bool keepL);
+// Out (lower tiles) = W^T W
+int lauum_lower(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo);
+int trmv_lower(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const double* y, double* out);
+int trmv_lower_T(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const double* a, double* out);
+int quad_logdet(gpb_handle* h, const double* v, int64_t n, const double* logdiag, double* out2);
+int predict_colreduce(gpb_handle* h, const double* A, int64_t lda, int64_t n, int64_t m, const double* a,
+                      const double* kdiag, double* mean, double* var);
+
+// ---- gpr.cu
+int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, double* grad_theta, double* grad_noise,
+            int want_grad);
+int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double* d_Xs, int64_t Ns, double* d_mean,
+                  double* d_var);
+
+}  // namespace gpb

@@ -1,0 +1,273 @@
+// kernel_eval.cuh -- device-side evaluation of a composite covariance expression and of its
+// hyper-parameter derivatives for ONE pair (x, x').  Shared by the assembly kernels, the fused
+// gradient reduction, the batched one-GP-per-CTA kernel and the SVGP kernels, so every path
+// evaluates k(x, x') with the same arithmetic.
+//
+// Arithmetic restated from GPflow 2.9.1 (un-vendored):
+//   gpflow/kernels/stationaries.py  SquaredExponential, RationalQuadratic, Matern12/32/52, Exponential
+//   gpflow/kernels/linears.py       Linear
+//   gpflow/kernels/periodic.py      Periodic
+//   gpflow/kernels/base.py          Sum, Product, active_dims slicing
+// Deliberate difference: distances use the direct form sum (x_d - x'_d)^2 rather
+// than GPflow's Gram form |x|^2 + |x'|^2 - 2 x.x', which is what a fused kernel computes naturally
+// and is the more accurate of the two; the oracle reproduces the Gram form to bound the gap.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/gpb200.h"
+
+namespace gpb {
+
+struct DevGroup {
+    int kind;
+    int ard_index;     // theta index of first ARD lengthscale, or -1
+    int period_index;  // theta index of period, or -1
+    int pad_;
+    double inv_period;
+    double w[GPB_MAX_DIMS];       // per-dim weight: mask (0/1) or ARD 1/l_d^2 (or 1/l_d for PERIODIC_ABS)
+    double inv_ls[GPB_MAX_DIMS];  // ARD only: 1/l_d (for the lengthscale derivative)
+    int ard_slot[GPB_MAX_DIMS];   // ARD only: k such that theta[ard_index + k] belongs to dim d
+};
+
+struct DevLeaf {
+    int kind;
+    int group;
+    int var_index, ls_index, alpha_index;
+    int arg_is_r;     // 1: group value (scaled) is r itself (PERIODIC_ABS); 0: it is r^2 (or the dot product)
+    double variance;
+    double scale;     // 1/l^2 (r^2 args), 1/l (r args), 1 for ARD / Linear
+    double inv_ls;    // 1/l (0 when no scalar lengthscale)
+    double alpha;
+};
+
+struct DevTerm {
+    int n_factors;
+    int leaf[GPB_MAX_FACTORS];
+};
+
+struct DevKernel {
+    int n_dims, n_params, n_groups, n_leaves, n_terms;
+    int pad_;
+    DevGroup groups[GPB_MAX_GROUPS];
+    DevLeaf leaves[GPB_MAX_LEAVES];
+    DevTerm terms[GPB_MAX_TERMS];
+};
+
+// ---- group value -------------------------------------------------------------------------------
+// s = reduction over active dims; when GRAD also returns ds/dperiod.
+template <int DP, bool GRAD>
+__device__ __forceinline__ double group_value(const DevGroup& g, const double (&xi)[DP], const double (&xj)[DP],
+                                              double& ds_dperiod) {
+    double s = 0.0;
+    if (GRAD) ds_dperiod = 0.0;
+    switch (g.kind) {
+        case GPB_GROUP_EUCLID: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                double t = xi[d] - xj[d];
+                s = fma(g.w[d] * t, t, s);
+            }
+        } break;
+        case GPB_GROUP_DOT: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) s = fma(g.w[d] * xi[d], xj[d], s);
+        } break;
+        case GPB_GROUP_PERIODIC_SQ: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                if (g.w[d] != 0.0) {
+                    double t = xi[d] - xj[d];
+                    double sn, cs;
+                    sincospi(t * g.inv_period, &sn, &cs);
+                    s = fma(g.w[d] * sn, sn, s);
+                    // d/dp sin^2(pi t/p) = 2 sin cos * (-pi t / p^2)
+                    if (GRAD) ds_dperiod = fma(g.w[d] * sn * cs, -2.0 * M_PI * t * g.inv_period * g.inv_period, ds_dperiod);
+                }
+            }
+        } break;
+        default: {  // GPB_GROUP_PERIODIC_ABS
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                if (g.w[d] != 0.0) {
+                    double t = xi[d] - xj[d];
+                    double sn, cs;
+                    sincospi(t * g.inv_period, &sn, &cs);
+                    s = fma(g.w[d], fabs(sn), s);
+                    if (GRAD) {
+                        double sg = (sn > 0.0) ? 1.0 : ((sn < 0.0) ? -1.0 : 0.0);
+                        ds_dperiod = fma(g.w[d] * sg * cs, -M_PI * t * g.inv_period * g.inv_period, ds_dperiod);
+                    }
+                }
+            }
+        } break;
+    }
+    return s;
+}
+
+// ---- leaf value ----------------------------------------------------------------------------------
+// v = variance * f(u), u = s * scale.  Returns v; when GRAD also
+//   f_out      = f(u)                       (dv/dvariance)
+//   dv_du_u    = variance * f'(u) * u       (finite everywhere; lengthscale derivative = that * c / l)
+//   dv_ds      = variance * f'(u) * scale   (chain to group parameters; 0 at the r = 0 singularity of
+//                                            Matern12/Exponential, matching TF's zero sub-gradient of
+//                                            maximum(r2, 1e-36))
+//   dv_dalpha  (RationalQuadratic)
+struct LeafOut {
+    double v, f, dv_du_u, dv_ds, dv_dalpha;
+};
+
+template <bool GRAD>
+__device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
+    LeafOut o;
+    o.dv_dalpha = 0.0;
+    const double u = s * lf.scale;
+    double f, fp_u, fp;  // f(u), f'(u)*u, f'(u)
+    switch (lf.kind) {
+        case GPB_LEAF_LINEAR: {
+            f = u; fp_u = u; fp = 1.0;
+        } break;
+        case GPB_LEAF_SE: {
+            f = exp(-0.5 * u);
+            fp = -0.5 * f; fp_u = fp * u;
+        } break;
+        case GPB_LEAF_RQ: {
+            const double b = 1.0 + 0.5 * u / lf.alpha;
+            const double lb = log(b);
+            f = exp(-lf.alpha * lb);
+            fp = -0.5 * f / b; fp_u = fp * u;
+            if (GRAD) o.dv_dalpha = lf.variance * f * (-lb + 0.5 * u / (lf.alpha * b));
+        } break;
+        default: {
+            // Matern family: needs r.  From an r^2 argument: r = sqrt(max(r2, 1e-36)) (GPflow K_r2);
+            // from a PERIODIC_ABS group the argument already is r (GPflow calls K_r directly).
+            const double r = lf.arg_is_r ? u : sqrt(fmax(u, 1e-36));
+            double df_dr;  // f'(r)
+            if (lf.kind == GPB_LEAF_MATERN12) {
+                f = exp(-r); df_dr = -f;
+            } else if (lf.kind == GPB_LEAF_EXPONENTIAL) {
+                f = exp(-0.5 * r); df_dr = -0.5 * f;
+            } else if (lf.kind == GPB_LEAF_MATERN32) {
+                const double s3 = 1.7320508075688772;
+                const double e = exp(-s3 * r);
+                f = (1.0 + s3 * r) * e; df_dr = -3.0 * r * e;
+            } else {  // MATERN52
+                const double s5 = 2.23606797749979;
+                const double e = exp(-s5 * r);
+                f = (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
+                df_dr = -(5.0 / 3.0) * r * (1.0 + s5 * r) * e;
+            }
+            if (lf.arg_is_r) {
+                fp = df_dr; fp_u = df_dr * r;
+            } else {
+                // d/du = df/dr / (2 r); times u = r^2 -> df/dr * r / 2
+                fp_u = 0.5 * df_dr * r;
+                fp = (u > 1e-36) ? 0.5 * df_dr / r : 0.0;
+                if (!(u > 1e-36)) fp_u = 0.0;
+            }
+        } break;
+    }
+    o.v = lf.variance * f;
+    if (GRAD) {
+        o.f = f;
+        o.dv_du_u = lf.variance * fp_u;
+        o.dv_ds = lf.variance * fp * lf.scale;
+    }
+    return o;
+}
+
+// ---- forward only: k(x, x') ----------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ double kernel_value(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP]) {
+    double total = 0.0;
+    int cached_group = -1;
+    double cached_s = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        double prod = 1.0;
+        for (int f = 0; f < tm.n_factors; ++f) {
+            const DevLeaf& lf = kp.leaves[tm.leaf[f]];
+            if (lf.group != cached_group) {
+                double dummy;
+                cached_s = group_value<DP, false>(kp.groups[lf.group], xi, xj, dummy);
+                cached_group = lf.group;
+            }
+            prod *= leaf_value<false>(lf, cached_s).v;
+        }
+        total += prod;
+    }
+    return total;
+}
+
+// ---- value + weighted parameter derivatives --------------------------------------------------------
+// acc[p] += wgt * dk/dtheta_p for every constrained parameter p; returns k.
+// acc is a per-thread array (local memory; dynamically indexed).
+template <int DP>
+__device__ __forceinline__ double kernel_value_grad(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP],
+                                                    double wgt, double* acc) {
+    double total = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        LeafOut lo[GPB_MAX_FACTORS];
+        double dsdp[GPB_MAX_FACTORS];
+        double prod = 1.0;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            if (f < tm.n_factors) {
+                const DevLeaf& lf = kp.leaves[tm.leaf[f]];
+                double s = group_value<DP, true>(kp.groups[lf.group], xi, xj, dsdp[f]);
+                lo[f] = leaf_value<true>(lf, s);
+                prod *= lo[f].v;
+            }
+        }
+        total += prod;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            if (f < tm.n_factors) {
+                double adj = wgt;
+#pragma unroll
+                for (int f2 = 0; f2 < GPB_MAX_FACTORS; ++f2)
+                    if (f2 != f && f2 < tm.n_factors) adj *= lo[f2].v;
+                const DevLeaf& lf = kp.leaves[tm.leaf[f]];
+                const DevGroup& g = kp.groups[lf.group];
+                acc[lf.var_index] += adj * lo[f].f;
+                if (lf.ls_index >= 0) {
+                    // u = s / l^2 -> du/dl = -2u/l ; u = s / l -> du/dl = -u/l
+                    const double c = lf.arg_is_r ? -1.0 : -2.0;
+                    acc[lf.ls_index] += adj * lo[f].dv_du_u * c * lf.inv_ls;
+                }
+                if (lf.alpha_index >= 0) acc[lf.alpha_index] += adj * lo[f].dv_dalpha;
+                if (g.period_index >= 0) acc[g.period_index] += adj * lo[f].dv_ds * dsdp[f];
+                if (g.ard_index >= 0) {
+                    // ARD: s = sum_d w_d q_d with w_d = 1/l_d^2 (or 1/l_d); ds/dl_d = -c' w_d q_d / l_d
+                    const bool per = (g.kind == GPB_GROUP_PERIODIC_SQ || g.kind == GPB_GROUP_PERIODIC_ABS);
+                    const double c = (g.kind == GPB_GROUP_PERIODIC_ABS) ? -1.0 : -2.0;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        if (g.w[d] != 0.0) {
+                            double tdiff = xi[d] - xj[d];
+                            double q;
+                            if (per) {
+                                double sn = sinpi(tdiff * g.inv_period);
+                                q = (g.kind == GPB_GROUP_PERIODIC_SQ) ? sn * sn : fabs(sn);
+                            } else {
+                                q = tdiff * tdiff;
+                            }
+                            acc[g.ard_index + g.ard_slot[d]] += adj * lo[f].dv_ds * c * g.w[d] * q * g.inv_ls[d];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return total;
+}
+
+// k(x, x) on the diagonal (gpflow K_diag): stationary -> variance, Linear -> sum w_d x_d^2.
+template <int DP>
+__device__ __forceinline__ double kernel_diag_value(const DevKernel& kp, const double (&xi)[DP]) {
+    return kernel_value<DP>(kp, xi, xi);
+}
+
+}  // namespace gpb
