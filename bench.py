@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native exact-GP engine.
+
+Metric (BASELINE.json): fp64 LML+grad evals/s at N=8192, D=8 (config C2: Multi-Input GPR,
+7 z-scored feature-return columns + z-scored time, kernel SquaredExponential + Matern52 + Linear,
+sigma^2 = 1e-2), one exact Cholesky-based log-marginal-likelihood + hyper-parameter gradient per
+step on one B200.  A single exact GP does not shard (north_star): with --gpus N > 1 every rank runs
+an independent replica of the same evaluation (restart / kernel-candidate parallelism), no
+data-path collective, `value` = evaluations of all ranks / max-over-ranks time ("weak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+JSON line keys: see the driver contract; `roofline` is the DMMA GEMM kernel (dominant kernel of the
+step) timed live with CUDA events on its launch stream through the engine's profiling hook;
+`cpu_baseline` is the CPU oracle (GPflow-equivalent restatement; GPflow 2.9.1 itself is not
+installable) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_C2, D_C2, NOISE_C2 = 8192, 8, 1e-2
+METRIC = "fp64 LML+grad evals/s (N=8192,D=8)"
+UNIT = "evals/s"
+
+
+def make_c2(seed=2, n=N_C2, d=D_C2):
+    """SURVEY.md 8d synthetic C2: factor-model daily returns, z-scored like
+    Multi-Input_GPR/utils/data_handler.py:160-169."""
+    rng = np.random.default_rng(seed)
+    f = rng.normal(0.0, 0.01, size=(n, 1))
+    beta = rng.uniform(0.5, 1.5, size=(1, d))
+    r = beta * f + rng.normal(0.0, 0.01, size=(n, d))
+    z = lambda a: (a - a.mean(0)) / a.std(0)
+    X = np.concatenate([z(r[:, 1:]), z(np.arange(n, dtype=np.float64)[:, None])], axis=1)
+    return np.ascontiguousarray(X), np.ascontiguousarray(z(r[:, :1]))
+
+
+def measured_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_source": "fallback", "fp64_tflops": 35.47, "fp64_source": "fallback"}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["hbm_gbs"] = float(mp["hbm_gbs"]); peaks["hbm_source"] = "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    try:
+        fp = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))
+        peaks["fp64_tflops"] = float(fp["fp64_dgemm_tflops"])
+        peaks["fp64_source"] = "profiles/FP64_PEAKS.json (cuBLAS DGEMM 8192^3 measured on this pool; MEASURED_PEAKS.json has no fp64 entry)"
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU arm: the oracle on the host cores ---------------------------------------------------------
+
+
+def cpu_lml_grad_once(X, Y):
+    from oracle import gpflow_oracle as O
+    k = O.Sum([O.Leaf("se"), O.Leaf("matern52"), O.Leaf("linear")])
+    t0 = time.perf_counter()
+    out = O.gpr_lml_and_grad(k, X, Y, NOISE_C2)
+    return time.perf_counter() - t0, out
+
+
+def cpu_threads():
+    try:
+        import torch
+        n = os.cpu_count() or 1
+        torch.set_num_threads(n)
+    except Exception:
+        n = os.cpu_count() or 1
+    return n
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  GPflow 2.9.1 /
+    TensorFlow cannot be installed (no network, not in /opt/wheelhouse), so this is the oracle
+    port (NumPy/SciPy LAPACK, analytic gradient, all host threads) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    X, Y = make_c2()
+    budget_s = 150.0
+    times = []
+    for _ in range(min(args.warmup, 1)):
+        cpu_lml_grad_once(X, Y)
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        dt, _ = cpu_lml_grad_once(X, Y)
+        times.append(dt)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    ms = 1e3 * float(np.mean(times))
+    val = 1e3 / ms
+    sample = f"{len(times)} full N=8192 evaluations (of --steps {args.steps}; capped at {budget_s:.0f} s), {min(args.warmup, 1)} warm-up"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "GPflow 2.9.1/TF 2.16 not installable here; CPU oracle port (oracle/gpflow_oracle.py) stands in for the reference"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "C2: exact GPR LML+grad, N=8192, D=8, kernel SquaredExponential+Matern52+Linear (all dims), "
+                        "noise 1e-2, synthetic z-scored factor returns seed 2",
+            "N": N_C2, "D": D_C2, "kernel": "SE+Matern52+Linear", "noise_variance": NOISE_C2,
+            "l2": "no explicit flush: per-step working set (K and L^-1, 2 x 537 MB) exceeds the 126 MB L2"}
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import portfoliooptgp_b200 as gpflow
+
+    X, Y = make_c2(seed=2 + rank)  # replicas: independent series per rank
+    k = gpflow.kernels.SquaredExponential() + gpflow.kernels.Matern52() + gpflow.kernels.Linear()
+    model = gpflow.models.GPR((X, Y), kernel=k, noise_variance=NOISE_C2)
+    eng = model._get_engine()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return model.lml_and_constrained_grads()
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lml, g, gn = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step
+
+    # ---- e2e: public API with HOST buffers: model construction (H2D of X, Y from pinned memory),
+    # objective + gradient through the closure optimizers.Scipy calls, D2H of loss + gradient
+    Xh = torch.from_numpy(X).pin_memory()
+    Yh = torch.from_numpy(Y).pin_memory()
+
+    def e2e_step():
+        m = gpflow.models.GPR((Xh, Yh), kernel=k, noise_variance=NOISE_C2)
+        loss, grads = m.training_loss_closure().value_and_grads(m.trainable_variables)
+        return loss, grads
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, grads = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * 1e3 * args.steps / ms_e2e
+    P = len(g)
+    h2d = X.nbytes + Y.nbytes
+    d2h = (2 + P + 1) * 8 + 4
+
+    # ---- roofline of the dominant kernel (DMMA GEMM), timed live with CUDA events per launch
+    peaks = measured_peaks()
+    eng.profile_enable(True)
+    prof_steps = max(1, min(args.steps, 3))
+    for _ in range(prof_steps):
+        step()
+    ms_cat, n_cat = eng.profile_read()
+    eng.profile_enable(False)
+    gemm_ms_step = ms_cat["gemm"] / prof_steps
+    flops_step = float(N_C2) ** 3  # N^3/3 factor + N^3/3 inverse + N^3/3 K^-1
+    achieved_tf = flops_step / (gemm_ms_step * 1e-3) / 1e12
+    asm_ms = ms_cat["assemble"] / prof_steps
+    asm_bytes = 8.0 * N_C2 * (N_C2 + 1) / 2 + 8.0 * D_C2 * N_C2 * 2
+    roofline = {"bound": "tensor", "kernel": "dgemm_kernel (DMMA.8x8x4): Cholesky trailing update + panel/inverse/K^-1 products",
+                "achieved": achieved_tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["fp64_tflops"],
+                "traffic": None, "peak_source": peaks["fp64_source"],
+                "launches_per_step": n_cat["gemm"] / prof_steps, "ms_per_step": gemm_ms_step,
+                "algorithmic_flops_per_step": flops_step}
+    breakdown = {c: ms_cat[c] / prof_steps for c in ms_cat if n_cat[c]}
+    assembly = {"bound": "hbm", "kernel": "assemble_kernel (lower tiles + noise)", "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "ms": asm_ms, "algorithmic_bytes": asm_bytes, "peak_source": peaks["hbm_source"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = cpu_threads()
+        dt, (l0, g0, n0) = cpu_lml_grad_once(X, Y)
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 full N=8192 evaluation of the same inputs (oracle/gpflow_oracle.py, NumPy/SciPy LAPACK, analytic gradient)",
+               "seconds": dt, "lml_rel_diff_vs_gpu": abs(l0 - lml) / abs(l0),
+               "grad_max_abs_diff_vs_gpu": float(np.max(np.abs(np.asarray(g0) - np.asarray(g))))}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "assembly_roofline": assembly,
+            "kernel_ms_per_step": breakdown, "cpu_baseline": cpu, "lml": lml}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,14 @@ int gpb_version(void);
 /* Number of engine kernels launched through this handle since creation (bench.py gpu_launches). */
 int64_t gpb_launch_count(gpb_handle* h);
 
+/* Optional kernel timing with CUDA events recorded on the handle's stream around each engine
+ * launch, by category (0 DMMA GEMM, 1 assembly, 2 Cholesky leaf, 3 fused gradient reduction,
+ * 4 vector kernels, 5 batched, 6 SVGP).  gpb_profile_read synchronises, returns the summed
+ * milliseconds and launch counts per category (arrays of 8) and resets the log.  bench.py's
+ * roofline numbers come from here; leave it off when timing end to end. */
+int gpb_profile_enable(gpb_handle* h, int on);
+int gpb_profile_read(gpb_handle* h, double* h_ms, int64_t* h_counts);
+
 /* ---- kernel expression ---------------------------------------------------------------------- */
 /* Replaces the kernel object handed to gpflow.models.GPR(kernel=...) (GPR/model_trainer.py:15). */
 int gpb_set_kernel(gpb_handle* h, const gpb_kernel_spec* spec);

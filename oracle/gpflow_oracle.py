@@ -346,9 +346,13 @@ def dK_dtheta(kernel, X) -> List[np.ndarray]:
             return [Xs @ Xs.T]
         return [np.outer(Xs[:, d_], Xs[:, d_]) for d_ in range(Xs.shape[1])]
     ls = np.broadcast_to(np.asarray(kernel.lengthscales, dtype=np.float64), (Xs.shape[1],))
-    diff = Xs[:, None, :] - Xs[None, :, :]
-    per_dim = np.square(diff / ls)
-    r2 = np.sum(per_dim, -1)
+    if np.ndim(kernel.lengthscales) == 0:
+        per_dim = None  # isotropic: only the [N,N] distance matrix is needed (no [N,N,D] tensor)
+        r2 = np.maximum(_sqdist(Xs / ls, None), 0.0)
+    else:
+        diff = Xs[:, None, :] - Xs[None, :, :]
+        per_dim = np.square(diff / ls)
+        r2 = np.sum(per_dim, -1)
     dk = _dk_dr2(kernel.kind, kernel.variance, r2, kernel.alpha)
     out = []
     if kernel.kind == "rq":

@@ -71,6 +71,8 @@ SIGNATURES = {
     "gpb_last_error": (C.c_char_p, [_P]),
     "gpb_set_stream": (_INT, [_P, _P]),
     "gpb_launch_count": (_I64, [_P]),
+    "gpb_profile_enable": (_INT, [_P, _INT]),
+    "gpb_profile_read": (_INT, [_P, _DP, C.POINTER(C.c_int64)]),
     "gpb_set_kernel": (_INT, [_P, C.POINTER(GpbKernelSpec)]),
     "gpb_assemble": (_INT, [_P, _DP, _P, _I64, _P, _I64, _INT, _P, _I64, _INT, _D]),
     "gpb_kdiag": (_INT, [_P, _DP, _P, _I64, _INT, _P]),
@@ -149,6 +151,18 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._lib.gpb_launch_count(self._h))
+
+    PROF_CATEGORIES = ("gemm", "assemble", "leaf", "grad_reduce", "vector", "batched", "svgp", "other")
+
+    def profile_enable(self, on: bool):
+        self._check(self._lib.gpb_profile_enable(self._h, int(bool(on))), "gpb_profile_enable")
+
+    def profile_read(self):
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.int64)
+        self._check(self._lib.gpb_profile_read(self._h, _as_dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))),
+                    "gpb_profile_read")
+        return ({c: float(m) for c, m in zip(self.PROF_CATEGORIES, ms)}, {c: int(n) for c, n in zip(self.PROF_CATEGORIES, cnt)})
 
     def set_kernel(self, spec: GpbKernelSpec, token=None):
         if token is not None and token == self._spec_token:

@@ -257,6 +257,7 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
     const int tiles_m = (int)((N + TILE - 1) / TILE), tiles_n = (int)((N2 + TILE - 1) / TILE);
     const int64_t nblk = (mode == 0) ? (int64_t)tiles_m * tiles_n : (int64_t)tiles_m * (tiles_m + 1) / 2;
     if (nblk > 0x7fffffffLL) return set_error(h, -2, "assemble: too many tiles");
+    ProfScope prof(h, PROF_ASSEMBLE, h->stream);
     GPB_DISPATCH_DP(D, (assemble_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(
                            kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n)));
     h->launches += 1;
@@ -278,6 +279,7 @@ int launch_grad_reduce(gpb_handle* h, const DevKernel& kp, const double* d_X, in
     const int64_t nblk = (int64_t)tiles * (tiles + 1) / 2;
     double* partial = workspace(h, BUF_RED, (size_t)nblk * (GPB_MAX_PARAMS + 1) * sizeof(double));
     if (!partial) return -1;
+    ProfScope prof(h, PROF_GRAD, h->stream);
     GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv, ldk,
                                                                                               d_alpha, partial)));
     int rc = check_cuda(h, cudaGetLastError(), "grad_reduce_kernel launch");

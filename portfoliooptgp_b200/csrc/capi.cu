@@ -66,6 +66,24 @@ double* pinned(gpb_handle* h, size_t bytes) {
     return h->h_pinned;
 }
 
+ProfScope::ProfScope(gpb_handle* h_, int cat, cudaStream_t st_) : h(h_), idx(-1), st(st_) {
+    if (!h->profile) return;
+    while (h->prof_pool.size() < h->prof_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->prof_pool.push_back(e);
+    }
+    gpb_handle::ProfRec r;
+    r.cat = cat; r.e0 = (int)h->prof_used; r.e1 = (int)h->prof_used + 1;
+    h->prof_used += 2;
+    cudaEventRecord(h->prof_pool[r.e0], st);
+    h->prof_recs.push_back(r);
+    idx = (int)h->prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof_pool[h->prof_recs[idx].e1], st);
+}
+
 static int validate_spec(gpb_handle* h, const gpb_kernel_spec* s) {
     if (s->n_dims < 1 || s->n_dims > GPB_MAX_DIMS) return set_error(h, -2, "kernel spec: n_dims=%d outside [1,%d]", s->n_dims, GPB_MAX_DIMS);
     if (s->n_params < 1 || s->n_params > GPB_MAX_PARAMS) return set_error(h, -2, "kernel spec: n_params=%d outside [1,%d]", s->n_params, GPB_MAX_PARAMS);
@@ -216,6 +234,7 @@ int gpb_destroy(gpb_handle* h) {
     for (int i = 0; i < 8; ++i)
         if (h->buf[i]) cudaFree(h->buf[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -232,6 +251,32 @@ int gpb_set_stream(gpb_handle* h, void* cuda_stream) {
 }
 
 int64_t gpb_launch_count(gpb_handle* h) { return h ? h->launches : -1; }
+
+int gpb_profile_enable(gpb_handle* h, int on) {
+    if (!h) return -1;
+    h->profile = (on != 0);
+    h->prof_recs.clear();
+    h->prof_used = 0;
+    return 0;
+}
+
+int gpb_profile_read(gpb_handle* h, double* h_ms, int64_t* h_counts) {
+    GPB_ENTER(h);
+    if (!h_ms || !h_counts) return set_error(h, -2, "profile_read: null pointer");
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "profile_read sync");
+    for (int c = 0; c < PROF_NCAT; ++c) { h_ms[c] = 0.0; h_counts[c] = 0; }
+    for (const auto& r : h->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_pool[r.e0], h->prof_pool[r.e1]) == cudaSuccess) {
+            h_ms[r.cat] += ms;
+            h_counts[r.cat] += 1;
+        }
+    }
+    h->prof_recs.clear();
+    h->prof_used = 0;
+    return 0;
+}
 
 int gpb_set_kernel(gpb_handle* h, const gpb_kernel_spec* spec) {
     if (!h || !spec) return -1;

@@ -64,6 +64,7 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
         if (e != cudaSuccess) return check_cuda(h, e, "leaf cudaFuncSetAttribute");
         attr_set = true;
     }
+    ProfScope prof(h, PROF_LEAF, h->stream);
     leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A + (int64_t)offset * lda + offset, lda,
                                                                      W + (int64_t)offset * ldw + offset, ldw, n, offset,
                                                                      logdiag, info);
@@ -187,6 +188,7 @@ __global__ void colsum_partials_kernel(const double* __restrict__ partial, int n
 
 int trmv_lower(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const double* y, double* out) {
     const int warps = 8;
+    ProfScope prof(h, PROF_VEC, h->stream);
     trmv_lower_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, 0, h->stream>>>(W, ldw, (int)n, y, out);
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "trmv_lower_kernel launch");
@@ -197,6 +199,7 @@ int trmv_lower_T(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const d
     double* partial = workspace(h, BUF_RED, (size_t)nch * n * sizeof(double));
     if (!partial) return -1;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)nch);
+    ProfScope prof(h, PROF_VEC, h->stream);
     trmvT_partial_kernel<<<grid, 128, 0, h->stream>>>(W, ldw, (int)n, a, partial);
     colsum_partials_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(partial, nch, (int)n, out);
     h->launches += 2;

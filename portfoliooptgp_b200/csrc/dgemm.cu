@@ -223,6 +223,7 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     p.tiles_n = tn;
     int64_t grid = p.tri ? (int64_t)tm * (tm + 1) / 2 : (int64_t)tm * tn;
     if (grid <= 0) return 0;
+    ProfScope prof(h, PROF_GEMM, stream);
     kern<<<(unsigned)grid, NT, SMEM, stream>>>(p);
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "dgemm_kernel launch");

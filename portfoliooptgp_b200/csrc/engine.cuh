@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "kernel_eval.cuh"
 
@@ -31,11 +32,26 @@ struct gpb_handle {
     size_t buf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double* h_pinned = nullptr;  // small pinned staging area for scalar results
     size_t h_pinned_bytes = 0;
+
+    // optional per-category kernel timing with CUDA events on the launch stream (bench.py roofline)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_pool;
+    struct ProfRec { int cat; int e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    size_t prof_used = 0;
 };
 
 namespace gpb {
 
 enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7 };
+
+enum ProfCat { PROF_GEMM = 0, PROF_ASSEMBLE = 1, PROF_LEAF = 2, PROF_GRAD = 3, PROF_VEC = 4, PROF_BATCHED = 5, PROF_SVGP = 6, PROF_NCAT = 8 };
+// RAII timer: records an event pair around the launches issued in its scope when h->profile is on.
+struct ProfScope {
+    gpb_handle* h; int idx; cudaStream_t st;
+    ProfScope(gpb_handle* h_, int cat, cudaStream_t st_);
+    ~ProfScope();
+};
 
 int set_error(gpb_handle* h, int code, const char* fmt, ...);
 int check_cuda(gpb_handle* h, cudaError_t e, const char* what);

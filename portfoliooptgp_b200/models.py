@@ -67,8 +67,12 @@ class GPModel(Module):
 
     # engine / kernel lowering ---------------------------------------------------------------
     def _get_engine(self) -> _capi.Engine:
+        # One engine (handle + grow-only workspaces) per device, shared by every model: the
+        # reference builds a fresh GPR per kernel candidate / rolling window / restart
+        # (GPR/model_trainer.py:15, Multi-Input_GPR/main.py:421), and each model re-binds its data and
+        # kernel expression at every evaluation, so nothing model-specific lives in the handle.
         if self._engine is None:
-            self._engine = _capi.Engine(self._device_index)
+            self._engine = ops.shared_engine(self._device_index)
         ops.sync_stream(self._engine)
         return self._engine
 
