@@ -1,83 +1,179 @@
-// block_chol.cuh -- CTA-cooperative dense kernels on a matrix resident in shared memory:
-// Cholesky factorisation, triangular inverse, triangular solves.  Shared by the 128x128 leaf of
-// the blocked Cholesky (cholesky.cu) and by the one-GP-per-CTA batched path (batched.cu)
-// (north_star subsystems 2 and 4).  All routines are called by every thread of the CTA.
+// block_chol.cuh -- CTA-cooperative dense kernels on ONE matrix resident in shared memory:
+// blocked Cholesky, in-place triangular inverse, warp-level DMMA tile products.  Shared by the
+// 128x128 leaf of the blocked Cholesky (cholesky.cu) and by the one-GP-per-CTA batched path
+// (batched.cu)  (north_star subsystems 2 and 4).  Every routine is called by all threads of the
+// CTA; blockDim.x must be a multiple of 32.
+//
+// Storage convention: row-major, leading dimension SLD = 132 doubles.  132 = 4 (mod 16) makes the
+// 64-bit DMMA fragment loads conflict-free for both k-contiguous and m-contiguous operands:
+// a half-warp touches addresses (g*132 + q) or (q*132 + g), g,q in 0..3 -> 16 distinct bank pairs.
+// Matrix sizes are padded to a multiple of 8 (the DMMA tile edge) with an identity block.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace gpb {
 
-// In-place lower Cholesky of the n x n matrix S (row-major, stride ld, only the lower triangle is
-// read).  Square-root-free elimination with ONE barrier per column: column j is kept unscaled
-// while it eliminates, all columns are scaled by 1/sqrt(d_j) at the end.  On exit S holds L in
-// its lower triangle; the strict upper triangle is zeroed.  *fail (shared) receives the 1-based
-// index of the first non-positive pivot (0 = none); the factorisation continues with the pivot
-// replaced by 1 so that no NaNs are produced.
-__device__ __forceinline__ void block_potrf_lower(double* S, int ld, int n, int* fail) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int tx = tid & 31, ty = tid >> 5, nwarps = nt >> 5;
-    if (tid == 0) *fail = 0;
-    __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        double d = S[j * ld + j];
-        if (!(d > 0.0)) {
-            // every thread sees the same value; thread 0 records and repairs
-            if (tid == 0 && *fail == 0) *fail = j + 1;
-            d = 1.0;
-        }
-        const double invd = 1.0 / d;
-        // trailing update with the unscaled column: S[i][k] -= S[i][j] * S[k][j] / d, j < k <= i
-        for (int i = j + 1 + ty; i < n; i += nwarps) {
-            const double lij = S[i * ld + j] * invd;
-            for (int k = j + 1 + tx; k <= i; k += 32) S[i * ld + k] = fma(-lij, S[k * ld + j], S[i * ld + k]);
-        }
-        __syncthreads();
-    }
-    // scale: L[i][j] = S[i][j] / sqrt(d_j) (i > j), L[j][j] = sqrt(d_j); zero the strict upper part
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        if (j > i) {
-            S[i * ld + j] = 0.0;
-        }
-    }
-    __syncthreads();
-    // diagonal last (columns are scaled by values derived from the diagonal)
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        if (j < i) {
-            double d = S[j * ld + j];
-            if (!(d > 0.0)) d = 1.0;
-            S[i * ld + j] *= rsqrt(d);
-        }
-    }
-    __syncthreads();
-    for (int j = tid; j < n; j += nt) {
-        double d = S[j * ld + j];
-        if (!(d > 0.0)) d = 1.0;
-        S[j * ld + j] = sqrt(d);
-    }
-    __syncthreads();
+constexpr int SLD = 132;          // shared-memory leading dimension (doubles)
+constexpr int TLD = 68;           // leading dimension of the 64 x 64 temporary used by the inverse
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ int packed_row(int i) { return i * (i + 1) / 2; }
+// acc (8x8 tile, DMMA C-fragment: thread holds C[g][2q], C[g][2q+1]) += sign * A[8 x klen] * B[klen x 8]
+//   A(m, k) at A[m * sam + k * sak],  B(k, n) at B[k * sbk + n * sbn];  klen multiple of 4.
+__device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const double* A, int sam, int sak, const double* B,
+                                              int sbk, int sbn, int klen, double sign) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const double* ap = A + g * sam + q * sak;
+    const double* bp = B + q * sbk + g * sbn;
+#pragma unroll 4
+    for (int k = 0; k < klen; k += 4) {
+        const double a = sign * ap[k * sak];
+        const double b = bp[k * sbk];
+        dmma_8x8x4(c0, c1, a, b);
+    }
+}
 
-// Wp (packed lower, row i at offset i(i+1)/2) = inverse of the lower-triangular L (row-major, ld).
-// Row-oriented forward substitution: row i of W from rows < i; one barrier per row, each column's
-// dot product split over 4 adjacent lanes.
-__device__ __forceinline__ void block_trtri_lower_packed(const double* L, int ld, int n, double* Wp) {
+// ---- Cholesky ----------------------------------------------------------------------------------------
+// In-place lower Cholesky of S (np x np, np multiple of 8, stride SLD); only the lower triangle is
+// read.  Right-looking with 8-wide panels: (a) warp 0 factors the 8x8 diagonal block in registers
+// (shuffles), (b) one thread per row solves the panel against it, (c) all warps apply the rank-8
+// trailing update with DMMA tiles.  On exit the lower triangle holds L, the strict upper triangle
+// of every 8x8 diagonal block is zero (the rest of the upper triangle is never written).
+// *fail (shared int) = 1-based index of the first non-positive pivot, 0 if none; a failing pivot is
+// replaced by 1 so that no NaNs propagate.  rdiag (shared, >= 8 doubles) is scratch.
+__device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* rdiag) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int part = tid & 3, jbase = tid >> 2, jstride = nt >> 2;
-    for (int i = 0; i < n; ++i) {
-        const double inv = 1.0 / L[i * ld + i];
-        for (int j0 = 0; j0 <= i; j0 += jstride) {
-            const int j = j0 + jbase;
-            double s = 0.0;
-            if (j < i) {
-                for (int k = j + part; k < i; k += 4) s = fma(L[i * ld + k], Wp[packed_row(k) + j], s);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (tid == 0) *fail = 0;
+    __syncthreads();
+    for (int p = 0; p < np; p += 8) {
+        // (a) diagonal block, warp 0: lane r (< 8) owns row r of the block
+        if (warp == 0) {
+            double a[8];
+            const int r = lane & 7;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = (c <= r) ? S[(p + r) * SLD + p + c] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double d = __shfl_sync(0xffffffffu, a[j], j);   // a_jj lives in lane j
+                if (!(d > 0.0)) {
+                    if (lane == 0 && *fail == 0) *fail = p + j + 1;
+                    d = 1.0;
+                }
+                const double rs = rsqrt(d);
+                // column j: l_rj = a_rj * rs (r > j), l_jj = d * rs
+                const double lrj = (r == j) ? d * rs : a[j] * rs;
+                a[j] = lrj;
+                // trailing update inside the block: a_rk -= l_rj * l_kj, j < k <= r
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, lrj, k);
+                    if (k <= r && r > j) a[k] = fma(-lrj, lkj, a[k]);
+                }
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (part == 0 && j <= i) Wp[packed_row(i) + j] = ((j == i) ? 1.0 : -s) * inv;
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) S[(p + r) * SLD + p + c] = (c <= r) ? a[c] : 0.0;
+                rdiag[r] = 1.0 / a[r];
+            }
+        }
+        __syncthreads();
+        const int m = np - p - 8;  // rows below the block
+        if (m > 0) {
+            // (b) panel solve: row i of A[p+8:, p:p+8] <- row * L_pp^-T
+            for (int i = tid; i < m; i += nt) {
+                double* row = S + (p + 8 + i) * SLD + p;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double v = row[c];
+#pragma unroll
+                    for (int c2 = 0; c2 < c; ++c2) v = fma(-x[c2], S[(p + c) * SLD + p + c2], v);
+                    x[c] = v * rdiag[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) row[c] = x[c];
+            }
+            __syncthreads();
+            // (c) trailing update, 8x8 tiles (ti >= tj) of the trailing matrix: C -= P_ti P_tj^T
+            const int mt = m >> 3;
+            const int g = lane >> 2, q = lane & 3;
+            int idx = 0;
+            for (int ti = 0; ti < mt; ++ti) {
+                for (int tj = 0; tj <= ti; ++tj, ++idx) {
+                    if (idx % nwarps != warp) continue;
+                    double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
+                    double2 c = *reinterpret_cast<double2*>(C);
+                    const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
+                    const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
+                    warp_tile_mma(c.x, c.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
+                    *reinterpret_cast<double2*>(C) = c;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- triangular inverse, in place ------------------------------------------------------------------------
+// S (np x np lower triangular, zero strict-upper inside 8x8 diagonal blocks) <- S^-1, np a multiple
+// of 8 and np <= 128.  Recursive doubling: invert the 8x8 diagonal blocks, then for b = 8, 16, 32, 64
+// combine neighbouring inverted blocks: W21 = -W22 (L21 W11), both products on DMMA tiles.
+// T (shared) is a 64 x TLD scratch.  Blocks that fall outside np are skipped (np need not be a power
+// of two: a trailing partial pair has a shorter second block).
+__device__ __forceinline__ void block_trtri_lower_inplace(double* S, int np, double* T) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    // base: 8x8 diagonal blocks, one warp each; lane c (< 8) solves column c of the inverse
+    for (int blk = warp; blk < (np >> 3); blk += nwarps) {
+        double* B = S + (blk * 8) * SLD + blk * 8;
+        double x[8];
+        const int c = lane & 7;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < r; ++k) v = fma(-B[r * SLD + k], x[k], v);   // x[k] = 0 for k < c
+            x[r] = (r >= c) ? v / B[r * SLD + r] : 0.0;
+        }
+        __syncwarp();
+        if (lane < 8) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) B[r * SLD + c] = x[r];
+        }
+    }
+    __syncthreads();
+    for (int b = 8; b < np; b <<= 1) {
+        const int npairs = (np + 2 * b - 1) / (2 * b);
+        const int bt = b >> 3;  // tiles per block edge
+        // T_pr = L21 W11  (W11 lower: k >= column tile)
+        for (int t = warp; t < npairs * bt * bt; t += nwarps) {
+            const int pr = t / (bt * bt), rem = t - pr * bt * bt, ti = rem / bt, tj = rem - ti * bt;
+            const int r0 = pr * 2 * b;
+            if (r0 + b + ti * 8 >= np) continue;   // second block shorter than b (or absent)
+            const double* L21 = S + (r0 + b + ti * 8) * SLD + r0;
+            const double* W11 = S + r0 * SLD + r0;
+            double c0 = 0.0, c1 = 0.0;
+            warp_tile_mma(c0, c1, L21 + tj * 8, SLD, 1, W11 + (tj * 8) * SLD + tj * 8, SLD, 1, b - tj * 8, 1.0);
+            double* out = T + (pr * b + ti * 8 + g) * TLD + tj * 8 + 2 * q;
+            *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
+        }
+        __syncthreads();
+        // W21 = -W22 T  (W22 lower: k <= row tile)
+        for (int t = warp; t < npairs * bt * bt; t += nwarps) {
+            const int pr = t / (bt * bt), rem = t - pr * bt * bt, ti = rem / bt, tj = rem - ti * bt;
+            const int r0 = pr * 2 * b;
+            if (r0 + b + ti * 8 >= np) continue;
+            const double* W22 = S + (r0 + b + ti * 8) * SLD + r0 + b;
+            const double* Tp = T + (pr * b) * TLD + tj * 8;
+            double c0 = 0.0, c1 = 0.0;
+            warp_tile_mma(c0, c1, W22, SLD, 1, Tp, TLD, 1, (ti + 1) * 8, -1.0);
+            double* out = S + (r0 + b + ti * 8 + g) * SLD + r0 + tj * 8 + 2 * q;
+            *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
         }
         __syncthreads();
     }

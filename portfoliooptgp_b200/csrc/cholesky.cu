@@ -20,39 +20,50 @@
 namespace gpb {
 
 constexpr int NB = 128;
-constexpr int LEAF_LD = NB + 1;
 constexpr int LEAF_THREADS = 512;
-constexpr size_t LEAF_SMEM = (size_t)(NB * LEAF_LD + NB * (NB + 1) / 2) * sizeof(double) + 16;
+constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + 16) * sizeof(double);
 
 // One CTA: L = chol(A_blk) in place, W_blk = L^-1, logdiag[blk] = sum log L_ii, info = first bad pivot.
+// The block lives in shared memory (stride SLD); factorisation and inverse run on DMMA tiles
+// (block_chol.cuh).  Blocks narrower than 128 are padded to a multiple of 8 with an identity.
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ W, int64_t ldw, int n, int offset,
                       double* __restrict__ logdiag, int* __restrict__ info) {
     extern __shared__ __align__(16) double sm[];
-    double* Ls = sm;
-    double* Wp = sm + NB * LEAF_LD;
-    int* fail = reinterpret_cast<int*>(Wp + NB * (NB + 1) / 2);
+    double* S = sm;
+    double* T = sm + NB * SLD;
+    double* rdiag = T + 64 * TLD;
+    int* fail = reinterpret_cast<int*>(rdiag + 8);
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < n * n; idx += LEAF_THREADS) {
-        const int i = idx / n, j = idx - i * n;
-        Ls[i * LEAF_LD + j] = (j <= i) ? A[(int64_t)i * lda + j] : 0.0;
+    const int np = (n + 7) & ~7;
+    for (int idx = tid; idx < np * NB; idx += LEAF_THREADS) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        if (j >= np) continue;
+        double v = 0.0;
+        if (i < n && j <= i) v = A[(int64_t)i * lda + j];
+        else if (i >= n && i == j) v = 1.0;
+        S[i * SLD + j] = v;
     }
     __syncthreads();
-    block_potrf_lower(Ls, LEAF_LD, n, fail);
+    block_potrf_lower(S, np, fail, rdiag);
     if (tid == 0 && *fail != 0) atomicCAS(info, 0, offset + *fail);
-    block_trtri_lower_packed(Ls, LEAF_LD, n, Wp);
-    for (int idx = tid; idx < n * n; idx += LEAF_THREADS) {
-        const int i = idx / n, j = idx - i * n;
-        A[(int64_t)i * lda + j] = Ls[i * LEAF_LD + j];
-        W[(int64_t)i * ldw + j] = (j <= i) ? Wp[packed_row(i) + j] : 0.0;
+    for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        if (j < n) A[(int64_t)i * lda + j] = S[i * SLD + j];
     }
     // sum of log-diagonal, fixed order: warp 0
     if (tid < 32) {
         double s = 0.0;
-        for (int i = tid; i < n; i += 32) s += log(Ls[i * LEAF_LD + i]);
+        for (int i = tid; i < n; i += 32) s += log(S[i * SLD + i]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
         if (tid == 0) logdiag[offset / NB] = s;
+    }
+    __syncthreads();
+    block_trtri_lower_inplace(S, np, T);
+    for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        if (j < n) W[(int64_t)i * ldw + j] = S[i * SLD + j];
     }
 }
 

@@ -27,7 +27,8 @@ struct GemmParams {
     int M, N, K;
     double alpha, beta;
     int tri, a_lower, a_upper, b_lower, b_upper;
-    int tiles_n;
+    int tiles_m, tiles_n;
+    int col_major_order, rev_m, rev_n;  // tile enumeration: heaviest k-ranges first (LPT)
     int vecA, vecB, vecC;
 };
 
@@ -117,8 +118,15 @@ dgemm_kernel(const GemmParams p) {
     if (p.tri) {
         tri_index(blockIdx.x, ti, tj);
     } else {
-        ti = blockIdx.x / p.tiles_n;
-        tj = blockIdx.x % p.tiles_n;
+        if (p.col_major_order) {
+            tj = blockIdx.x / p.tiles_m;
+            ti = blockIdx.x % p.tiles_m;
+        } else {
+            ti = blockIdx.x / p.tiles_n;
+            tj = blockIdx.x % p.tiles_n;
+        }
+        if (p.rev_m) ti = p.tiles_m - 1 - ti;
+        if (p.rev_n) tj = p.tiles_n - 1 - tj;
     }
     const int row0 = ti * BM, col0 = tj * BN;
     int kbeg = 0, kend = p.K;
@@ -221,6 +229,7 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     }
     const int tm = (p.M + BM - 1) / BM, tn = (p.N + BN - 1) / BN;
     p.tiles_n = tn;
+    p.tiles_m = tm;
     int64_t grid = p.tri ? (int64_t)tm * (tm + 1) / 2 : (int64_t)tm * tn;
     if (grid <= 0) return 0;
     ProfScope prof(h, PROF_GEMM, stream);
@@ -236,7 +245,12 @@ static int launch_layout(gpb_handle* h, const GemmParams& p, cudaStream_t stream
                                     : ((int64_t)((p.M + 127) / 128) * ((p.N + 127) / 128));
     if (big_tiles >= h->sm_count)
         return launch_cfg<128, 128, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
-    return launch_cfg<64, 64, 16, 32, 32, 3, AKC, BKC>(h, p, stream);
+    const int64_t mid_tiles = p.tri ? ((int64_t)((p.M + 63) / 64) * ((p.M + 63) / 64 + 1) / 2)
+                                    : ((int64_t)((p.M + 63) / 64) * ((p.N + 63) / 64));
+    if (mid_tiles >= h->sm_count)
+        return launch_cfg<64, 64, 16, 32, 32, 3, AKC, BKC>(h, p, stream);
+    // latency-bound regime (the bottom of the Cholesky recursion): spread over as many SMs as possible
+    return launch_cfg<32, 32, 16, 16, 16, 3, AKC, BKC>(h, p, stream);
 }
 
 int launch_gemm(gpb_handle* h, const GemmArgs& a, cudaStream_t stream) {
@@ -249,7 +263,10 @@ int launch_gemm(gpb_handle* h, const GemmArgs& a, cudaStream_t stream) {
     p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
     p.alpha = a.alpha; p.beta = a.beta;
     p.tri = a.tri; p.a_lower = a.a_lower; p.a_upper = a.a_upper; p.b_lower = a.b_lower; p.b_upper = a.b_upper;
-    p.tiles_n = 0;
+    p.tiles_n = 0; p.tiles_m = 0;
+    p.col_major_order = (a.b_upper || a.b_lower) ? 1 : 0;
+    p.rev_m = a.a_lower ? 1 : 0;
+    p.rev_n = a.b_upper ? 1 : 0;
     auto aligned = [](const void* ptr, int64_t ld) { return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && ((ld & 1) == 0); };
     p.vecA = aligned(a.A, a.lda);
     p.vecB = aligned(a.B, a.ldb);
