@@ -156,6 +156,23 @@ int gpb_gpr_lml_grad(gpb_handle* h, const double* h_theta, double noise_variance
 int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Xs,
                       int64_t Ns, double* d_mean, double* d_var);
 
+/* ---- batched independent small GPs (north_star subsystem 4) -------------------------------------
+ * One GP per CTA, K resident in shared memory (N <= 128).  Replaces the sequential rolling re-fit
+ * loop Multi-Input_GPR/main.py:414-456 x restarts models/model_trainer.py:26-48: B independent
+ * GPR objective(+gradient) evaluations sharing one kernel expression (gpb_set_kernel).
+ * All pointers are DEVICE pointers: d_X [B,N,D], d_Yc [B,N], d_theta [B,n_params] (constrained),
+ * d_noise [B]; d_out [B, 2 + n_params] = {lml, dlml/dnoise, dlml/dtheta...} (gradient entries are
+ * written only when want_grad); d_info [B]: 0 ok, >0 first non-positive pivot, <0 bad lengthscale.
+ * Asynchronous on the handle's stream. */
+int gpb_batched_lml_grad(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                         const double* d_noise, int64_t B, int64_t N, int D, double* d_out,
+                         int32_t* d_info, int want_grad);
+/* Batched GPR.predict_f(full_cov=False) at Ns new points per GP (Multi-Input_GPR/main.py:434 takes
+ * the last row): d_Xs [B,Ns,D] -> d_mean, d_var [B,Ns]. */
+int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                          const double* d_noise, int64_t B, int64_t N, int D, const double* d_Xs,
+                          int64_t Ns, double* d_mean, double* d_var, int32_t* d_info);
+
 #ifdef __cplusplus
 }
 #endif

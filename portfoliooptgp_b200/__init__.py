@@ -12,3 +12,5 @@ from .config import default_float, default_jitter  # noqa: F401
 from ._capi import CholeskyError, EngineError  # noqa: F401
 
 __version__ = "0.1.0"
+from . import batched  # noqa: E402,F401
+from .batched import BatchedGPR, lockstep_lbfgsb  # noqa: E402,F401

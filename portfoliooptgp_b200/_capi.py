@@ -84,6 +84,8 @@ SIGNATURES = {
     "gpb_gpr_lml": (_INT, [_P, _DP, _D, _DP]),
     "gpb_gpr_lml_grad": (_INT, [_P, _DP, _D, _DP, _DP, _DP]),
     "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
+    "gpb_batched_lml_grad": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
+    "gpb_batched_predict_f": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
 }
 
 
@@ -218,3 +220,14 @@ class Engine:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         self._check(self._lib.gpb_gpr_predict_f(self._h, _as_dp(theta), float(noise), _P(dXs), Ns, _P(dmean), _P(dvar)),
                     "gpb_gpr_predict_f")
+
+    # -- batched small GPs -----------------------------------------------------------------------
+    def batched_lml_grad(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dout: int,
+                         dinfo: int, want_grad: bool = True):
+        self._check(self._lib.gpb_batched_lml_grad(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dout),
+                                                   _P(dinfo), int(bool(want_grad))), "gpb_batched_lml_grad")
+
+    def batched_predict_f(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dXs: int, Ns: int,
+                          dmean: int, dvar: int, dinfo: int):
+        self._check(self._lib.gpb_batched_predict_f(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dXs),
+                                                    Ns, _P(dmean), _P(dvar), _P(dinfo)), "gpb_batched_predict_f")

@@ -1,0 +1,276 @@
+"""Batched independent small GPs (north_star subsystem 4; BASELINE config C3).
+
+The reference fits one small GPR per (asset, rolling window, restart) in nested Python loops
+(Multi-Input_GPR/main.py:414-456 calling models/model_trainer.py:17-54): fresh
+``gpflow.models.GPR((X[:i], Y[:i]), deepcopy(kernel), noise_variance=...)`` + ``Scipy().minimize``
++ ``predict_f(...)[-1]`` each time.  ``BatchedGPR`` holds B such problems that share one kernel
+*expression* (each with its own hyper-parameter values) and evaluates all objectives and
+gradients in one launch (one GP per CTA, covariance resident in shared memory), and
+``lockstep_lbfgsb`` advances B SciPy L-BFGS-B instances together -- same compiled ``setulb``
+reverse-communication loop as ``scipy.optimize.minimize(method="L-BFGS-B")``, so the iterates of
+every problem are SciPy's own -- with one batched objective launch per round.
+
+Across GPUs the batch is split into contiguous blocks, one per rank, with no communication during
+evaluation and one final gather (``shard_range`` / ``gather_results``).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.optimize
+import torch
+
+from . import ops
+from .base import Softplus
+from .kernels import Kernel, compile_kernel
+from .likelihoods import DEFAULT_VARIANCE_LOWER_BOUND
+
+
+# ---- lock-step L-BFGS-B ------------------------------------------------------------------------------
+
+
+def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]], X0: np.ndarray,
+                    maxiter: int = 15000, maxfun: int = 15000, maxcor: int = 10, ftol: float = 2.2204460492503131e-09,
+                    gtol: float = 1e-5, maxls: int = 20) -> List[scipy.optimize.OptimizeResult]:
+    """Minimise B independent problems with SciPy's L-BFGS-B, advancing them in lock step.
+
+    ``fun_batch(X [b, n], idx [b]) -> (f [b], g [b, n])`` evaluates the problems ``idx`` at ``X``.
+    Each problem runs the reverse-communication loop of ``scipy.optimize._lbfgsb_py._minimize_lbfgsb``
+    (same ``_lbfgsb.setulb``, same defaults, same stopping rules); whenever a problem asks for
+    f and g it is parked until every active problem has asked, then one ``fun_batch`` call serves
+    them all."""
+    from scipy.optimize import _lbfgsb_py as _lb
+    _lbfgsb = _lb._lbfgsb
+    int_dtype = np.int64 if getattr(_lb, "HAS_ILP64", False) else np.int32
+    X0 = np.ascontiguousarray(X0, dtype=np.float64)
+    B, n = X0.shape
+    m = maxcor
+    factr = ftol / np.finfo(float).eps
+
+    class _State:
+        __slots__ = ("x", "f", "g", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave", "nit", "nfev", "done")
+
+    states = []
+    nbd = np.zeros(n, dtype=int_dtype)
+    low = np.zeros(n, dtype=np.float64)
+    up = np.zeros(n, dtype=np.float64)
+    for b in range(B):
+        s = _State()
+        s.x = np.array(X0[b], dtype=np.float64)
+        s.f = np.array(0.0, dtype=np.float64)
+        s.g = np.zeros((n,), dtype=np.float64)
+        s.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        s.iwa = np.zeros(3 * n, dtype=int_dtype)
+        s.task = np.zeros(2, dtype=int_dtype)
+        s.ln_task = np.zeros(2, dtype=int_dtype)
+        s.lsave = np.zeros(4, dtype=int_dtype)
+        s.isave = np.zeros(44, dtype=int_dtype)
+        s.dsave = np.zeros(29, dtype=np.float64)
+        s.nit = 0
+        s.nfev = 0
+        s.done = False
+        states.append(s)
+
+    active = list(range(B))
+    while active:
+        waiting = []
+        for b in active:
+            s = states[b]
+            while True:  # advance until this problem needs f,g or stops
+                _lbfgsb.setulb(m, s.x, low, up, nbd, s.f, s.g, factr, gtol, s.wa, s.iwa, s.task, s.lsave, s.isave,
+                               s.dsave, maxls, s.ln_task)
+                if s.task[0] == 3:
+                    waiting.append(b)
+                    break
+                elif s.task[0] == 1:
+                    s.nit += 1
+                    if s.nit >= maxiter:
+                        s.task[0] = 5
+                        s.task[1] = 504
+                    elif s.nfev > maxfun:
+                        s.task[0] = 5
+                        s.task[1] = 502
+                else:
+                    s.done = True
+                    break
+        if not waiting:
+            break
+        idx = np.asarray(waiting, dtype=np.int64)
+        Xb = np.stack([states[b].x for b in waiting])
+        fb, gb = fun_batch(Xb, idx)
+        for k, b in enumerate(waiting):
+            s = states[b]
+            s.f = np.array(float(fb[k]), dtype=np.float64)
+            s.g = np.ascontiguousarray(gb[k], dtype=np.float64)
+            s.nfev += 1
+        active = waiting
+
+    results = []
+    for s in states:
+        if s.task[0] == 4:
+            warnflag = 0
+        elif s.nfev > maxfun or s.nit >= maxiter:
+            warnflag = 1
+        else:
+            warnflag = 2
+        msg = _lb.status_messages[s.task[0]] + ": " + _lb.task_messages[s.task[1]]
+        results.append(scipy.optimize.OptimizeResult(fun=float(s.f), jac=s.g, nfev=s.nfev, njev=s.nfev, nit=s.nit,
+                                                     status=warnflag, message=msg, x=s.x, success=(warnflag == 0)))
+    return results
+
+
+# ---- multi-GPU partitioning -----------------------------------------------------------------------------
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block partition of ``total`` independent GPs: rank r owns [lo, hi)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank result rows ([B_local, C]) into [total, C] (the single collective of
+    the C3 path).  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    maxn = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((maxn,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+# ---- the batched model ------------------------------------------------------------------------------------
+
+
+class BatchedGPR:
+    """B independent exact GPs (N <= 128 rows each) sharing one kernel expression.
+
+    X [B,N,D], Y [B,N] (or [B,N,1]); ``kernel`` gives the expression, the trainable flags and the
+    initial hyper-parameters of every GP; ``noise_variance`` scalar or [B] (the restart grid of
+    models/model_trainer.py:26 is a [B] vector); ``train_noise`` mirrors
+    ``set_trainable(model.likelihood, True/False)``."""
+
+    def __init__(self, X, Y, kernel: Kernel, noise_variance=1.0, train_noise: bool = True, device=None):
+        self.device_index = ops.cuda_device_index(device)
+        self.X = ops.to_device(X, self.device_index)
+        if self.X.ndim != 3:
+            raise ValueError("X must be [B, N, D]")
+        self.B, self.N, self.D = (int(v) for v in self.X.shape)
+        Yd = ops.to_device(Y, self.device_index)
+        if Yd.ndim == 3:
+            if Yd.shape[2] != 1:
+                raise NotImplementedError("single-output GPs only")
+            Yd = Yd[:, :, 0]
+        if tuple(Yd.shape) != (self.B, self.N):
+            raise ValueError("Y must be [B, N]")
+        self.Y = Yd.contiguous()
+        if self.N > 128:
+            raise ValueError("the one-GP-per-CTA path holds K in shared memory: N <= 128")
+        self.kernel = kernel
+        self.compiled = compile_kernel(kernel, self.D)
+        self.P = self.compiled.n_params
+        theta0 = self.compiled.theta()
+        self.theta = np.tile(theta0[None, :], (self.B, 1))                     # constrained, [B,P]
+        self.noise = np.broadcast_to(np.asarray(noise_variance, dtype=np.float64), (self.B,)).copy()
+        self.train_noise = bool(train_noise)
+        # which theta slots are trainable (by the template kernel's Parameter flags)
+        mask = np.zeros(self.P, dtype=bool)
+        for p, o in zip(self.compiled.params, self.compiled.offsets):
+            mask[o:o + max(1, p.size)] = p.trainable
+        self.trainable_mask = mask
+        self._theta_tf = Softplus(0.0)
+        self._noise_tf = Softplus(DEFAULT_VARIANCE_LOWER_BOUND)
+        self._engine = ops.shared_engine(self.device_index)
+        self._out = torch.empty((self.B, 2 + self.P), dtype=torch.float64, device=self.X.device)
+        self._info = torch.zeros((self.B,), dtype=torch.int32, device=self.X.device)
+
+    # -- raw device evaluation ---------------------------------------------------------------------
+    def _launch(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool):
+        eng = self._engine
+        ops.sync_stream(eng)
+        eng.set_kernel(self.compiled.spec, self.compiled.token)
+        dev = self.X.device
+        th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev, non_blocking=True)
+        nz = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev, non_blocking=True)
+        if idx is None:
+            Xb, Yb, b = self.X, self.Y, self.B
+        else:
+            it = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(dev)
+            Xb, Yb, b = self.X.index_select(0, it).contiguous(), self.Y.index_select(0, it).contiguous(), len(idx)
+        out, info = self._out[:b], self._info[:b]
+        eng.batched_lml_grad(Xb.data_ptr(), Yb.data_ptr(), th.data_ptr(), nz.data_ptr(), b, self.N, self.D,
+                             out.data_ptr(), info.data_ptr(), want_grad)
+        return out, info
+
+    def lml_and_grads(self, theta: Optional[np.ndarray] = None, noise: Optional[np.ndarray] = None,
+                      idx: Optional[np.ndarray] = None, want_grad: bool = True):
+        """(lml [b], dlml/dtheta [b,P] constrained, dlml/dnoise [b], info [b]) as numpy arrays."""
+        theta = self.theta if theta is None else theta
+        noise = self.noise if noise is None else noise
+        if idx is not None and theta.shape[0] == self.B:
+            theta, noise = theta[idx], noise[idx]
+        out, info = self._launch(theta, noise, idx, want_grad)
+        o = out.cpu().numpy()
+        return o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), info.cpu().numpy()
+
+    # -- optimisation in unconstrained space ---------------------------------------------------------
+    def _pack(self) -> np.ndarray:
+        cols = [self._theta_tf.inverse(self.theta[:, self.trainable_mask])]
+        if self.train_noise:
+            cols.append(self._noise_tf.inverse(self.noise)[:, None])
+        return np.concatenate(cols, axis=1)
+
+    def _unpack(self, U: np.ndarray, idx: np.ndarray):
+        nt = int(self.trainable_mask.sum())
+        theta = self.theta[idx].copy()
+        theta[:, self.trainable_mask] = self._theta_tf.forward(U[:, :nt])
+        noise = self._noise_tf.forward(U[:, nt]) if self.train_noise else self.noise[idx].copy()
+        return theta, noise
+
+    def loss_and_grads_unconstrained(self, U: np.ndarray, idx: np.ndarray):
+        """training_loss (= -LML) and its gradient w.r.t. the packed unconstrained variables."""
+        theta, noise = self._unpack(U, idx)
+        lml, gth, gnz, info = self.lml_and_grads(theta, noise, idx)
+        nt = int(self.trainable_mask.sum())
+        g = -gth[:, self.trainable_mask] * self._theta_tf.forward_grad(U[:, :nt])
+        if self.train_noise:
+            g = np.concatenate([g, (-gnz * self._noise_tf.forward_grad(U[:, nt]))[:, None]], axis=1)
+        f = -lml
+        bad = info != 0
+        if np.any(bad):  # non-PD at a trial point: GPflow would raise; here the line search backs off
+            f = np.where(bad, np.inf, f)
+            g = np.where(bad[:, None], 0.0, g)
+        return f, g
+
+    def fit(self, maxiter: int = 15000, **lbfgs_kwargs) -> List[scipy.optimize.OptimizeResult]:
+        """Scipy().minimize(model.training_loss, model.trainable_variables) for every GP, lock step."""
+        U0 = self._pack()
+        res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter, **lbfgs_kwargs)
+        U = np.stack([r.x for r in res])
+        self.theta, self.noise = self._unpack(U, np.arange(self.B))
+        return res
+
+    def predict_f(self, Xnew):
+        """Per-GP predict_f(Xnew[b], full_cov=False): Xnew [B,Ns,D] -> (mean [B,Ns], var [B,Ns]) on device."""
+        Xs = ops.to_device(Xnew, self.device_index)
+        if Xs.ndim != 3 or Xs.shape[0] != self.B or Xs.shape[2] != self.D:
+            raise ValueError("Xnew must be [B, Ns, D]")
+        Ns = int(Xs.shape[1])
+        eng = self._engine
+        ops.sync_stream(eng)
+        eng.set_kernel(self.compiled.spec, self.compiled.token)
+        dev = self.X.device
+        th = torch.from_numpy(np.ascontiguousarray(self.theta)).to(dev)
+        nz = torch.from_numpy(np.ascontiguousarray(self.noise)).to(dev)
+        mean = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
+        var = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
+        eng.batched_predict_f(self.X.data_ptr(), self.Y.data_ptr(), th.data_ptr(), nz.data_ptr(), self.B, self.N, self.D,
+                              Xs.data_ptr(), Ns, mean.data_ptr(), var.data_ptr(), self._info.data_ptr())
+        return mean, var

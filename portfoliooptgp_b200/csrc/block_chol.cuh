@@ -8,6 +8,11 @@
 // 64-bit DMMA fragment loads conflict-free for both k-contiguous and m-contiguous operands:
 // a half-warp touches addresses (g*132 + q) or (q*132 + g), g,q in 0..3 -> 16 distinct bank pairs.
 // Matrix sizes are padded to a multiple of 8 (the DMMA tile edge) with an identity block.
+//
+// Measured on B200 (tools/leaf_prof.cu): dependent DMMA 26 cycles, fp64 divide 131 cycles, a 64-bit
+// shuffle + add 85 cycles.  The pivot chain is therefore kept free of shuffles and divides: warp 0
+// factors each 8x8 diagonal block redundantly in registers (rsqrt per pivot), inverts it, and the
+// panel solve becomes a DMMA product with that inverse.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -15,6 +20,8 @@ namespace gpb {
 
 constexpr int SLD = 132;          // shared-memory leading dimension (doubles)
 constexpr int TLD = 68;           // leading dimension of the 64 x 64 temporary used by the inverse
+constexpr int DLD = 12;           // leading dimension of the stored 8x8 diagonal-block inverses
+constexpr int DINV_DOUBLES = 16 * 8 * DLD;   // 16 diagonal blocks of a 128 x 128 matrix
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -37,80 +44,96 @@ __device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const doub
 }
 
 // ---- Cholesky ----------------------------------------------------------------------------------------
-// In-place lower Cholesky of S (np x np, np multiple of 8, stride SLD); only the lower triangle is
-// read.  Right-looking with 8-wide panels: (a) warp 0 factors the 8x8 diagonal block in registers
-// (shuffles), (b) one thread per row solves the panel against it, (c) all warps apply the rank-8
-// trailing update with DMMA tiles.  On exit the lower triangle holds L, the strict upper triangle
-// of every 8x8 diagonal block is zero (the rest of the upper triangle is never written).
+// In-place lower Cholesky of S (np x np, np multiple of 8, np <= 128, stride SLD); only the lower
+// triangle is read.  Right-looking with 8-wide panels:
+//   (a) warp 0 factors the 8x8 diagonal block and inverts the factor, entirely in registers
+//       (every lane redundantly: no shuffles on the pivot chain), stores L_pp and M = L_pp^-1;
+//   (b) panel  <- panel * M^T        one DMMA tile product per 8 rows;
+//   (c) trailing update C -= P P^T   DMMA tiles of the lower triangle, all warps.
+// On exit the lower triangle holds L, the strict upper triangle of every 8x8 diagonal block is zero
+// (the rest of the upper triangle is never written), and dinv (shared, DINV_DOUBLES) holds the
+// inverses of the diagonal blocks (block b at dinv + b*8*DLD, row-major, stride DLD, zero upper).
 // *fail (shared int) = 1-based index of the first non-positive pivot, 0 if none; a failing pivot is
-// replaced by 1 so that no NaNs propagate.  rdiag (shared, >= 8 doubles) is scratch.
-__device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* rdiag) {
+// replaced by 1 so that no NaNs propagate.
+__device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* dinv) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int g = lane >> 2, q = lane & 3;
     if (tid == 0) *fail = 0;
     __syncthreads();
     for (int p = 0; p < np; p += 8) {
-        // (a) diagonal block, warp 0: lane r (< 8) owns row r of the block
+        double* M = dinv + (p >> 3) * 8 * DLD;
         if (warp == 0) {
-            double a[8];
-            const int r = lane & 7;
+            // (a) all 32 lanes hold the whole lower triangle (broadcast loads) and run the same code
+            double a[8][8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] = (c <= r) ? S[(p + r) * SLD + p + c] : 0.0;
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) a[r][c] = S[(p + r) * SLD + p + c];
+            double rs[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);   // a_jj lives in lane j
+                double d = a[j][j];
                 if (!(d > 0.0)) {
                     if (lane == 0 && *fail == 0) *fail = p + j + 1;
                     d = 1.0;
                 }
-                const double rs = rsqrt(d);
-                // column j: l_rj = a_rj * rs (r > j), l_jj = d * rs
-                const double lrj = (r == j) ? d * rs : a[j] * rs;
-                a[j] = lrj;
-                // trailing update inside the block: a_rk -= l_rj * l_kj, j < k <= r
+                rs[j] = rsqrt(d);
+                a[j][j] = d * rs[j];
 #pragma unroll
-                for (int k = j + 1; k < 8; ++k) {
-                    const double lkj = __shfl_sync(0xffffffffu, lrj, k);
-                    if (k <= r && r > j) a[k] = fma(-lrj, lkj, a[k]);
+                for (int r = j + 1; r < 8; ++r) a[r][j] *= rs[j];
+#pragma unroll
+                for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+                    for (int k = j + 1; k <= r; ++k) a[r][k] = fma(-a[r][j], a[k][j], a[r][k]);
+            }
+            // inverse of the factor: lane c (mod 8) solves column c; 1/L_jj = rs[j]
+            double x[8];
+            const int c = lane & 7;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < r; ++k) v = fma(-a[r][k], x[k], v);
+                x[r] = (r >= c) ? v * rs[r] : 0.0;
+            }
+            // write back: lane r (< 8) writes row r of L (static register indices via the unrolled select)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (lane == r) {
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) S[(p + r) * SLD + p + cc] = (cc <= r) ? a[r][cc] : 0.0;
                 }
             }
             if (lane < 8) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) S[(p + r) * SLD + p + c] = (c <= r) ? a[c] : 0.0;
-                rdiag[r] = 1.0 / a[r];
+                for (int r = 0; r < 8; ++r) M[r * DLD + c] = x[r];
             }
         }
         __syncthreads();
         const int m = np - p - 8;  // rows below the block
         if (m > 0) {
-            // (b) panel solve: row i of A[p+8:, p:p+8] <- row * L_pp^-T
-            for (int i = tid; i < m; i += nt) {
-                double* row = S + (p + 8 + i) * SLD + p;
-                double x[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double v = row[c];
-#pragma unroll
-                    for (int c2 = 0; c2 < c; ++c2) v = fma(-x[c2], S[(p + c) * SLD + p + c2], v);
-                    x[c] = v * rdiag[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) row[c] = x[c];
+            const int mt = m >> 3;
+            // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
+            for (int ti = warp; ti < mt; ti += nwarps) {
+                double* Pt = S + (p + 8 + ti * 8) * SLD + p;
+                double c0 = 0.0, c1 = 0.0;
+                warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+                __syncwarp();
+                *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
             }
             __syncthreads();
             // (c) trailing update, 8x8 tiles (ti >= tj) of the trailing matrix: C -= P_ti P_tj^T
-            const int mt = m >> 3;
-            const int g = lane >> 2, q = lane & 3;
             int idx = 0;
             for (int ti = 0; ti < mt; ++ti) {
                 for (int tj = 0; tj <= ti; ++tj, ++idx) {
                     if (idx % nwarps != warp) continue;
                     double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
-                    double2 c = *reinterpret_cast<double2*>(C);
+                    double2 cc = *reinterpret_cast<double2*>(C);
                     const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
                     const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
-                    warp_tile_mma(c.x, c.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
-                    *reinterpret_cast<double2*>(C) = c;
+                    warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
+                    *reinterpret_cast<double2*>(C) = cc;
                 }
             }
             __syncthreads();
@@ -119,32 +142,19 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
 }
 
 // ---- triangular inverse, in place ------------------------------------------------------------------------
-// S (np x np lower triangular, zero strict-upper inside 8x8 diagonal blocks) <- S^-1, np a multiple
-// of 8 and np <= 128.  Recursive doubling: invert the 8x8 diagonal blocks, then for b = 8, 16, 32, 64
-// combine neighbouring inverted blocks: W21 = -W22 (L21 W11), both products on DMMA tiles.
+// S (np x np lower triangular) <- S^-1, np a multiple of 8 and np <= 128, given the inverses of its
+// 8x8 diagonal blocks in dinv (as left by block_potrf_lower).  Recursive doubling: for b = 8, 16,
+// 32, 64 combine neighbouring inverted blocks: W21 = -W22 (L21 W11), both products on DMMA tiles.
 // T (shared) is a 64 x TLD scratch.  Blocks that fall outside np are skipped (np need not be a power
 // of two: a trailing partial pair has a shorter second block).
-__device__ __forceinline__ void block_trtri_lower_inplace(double* S, int np, double* T) {
+__device__ __forceinline__ void block_trtri_lower_inplace(double* S, int np, double* T, const double* dinv) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
-    // base: 8x8 diagonal blocks, one warp each; lane c (< 8) solves column c of the inverse
-    for (int blk = warp; blk < (np >> 3); blk += nwarps) {
-        double* B = S + (blk * 8) * SLD + blk * 8;
-        double x[8];
-        const int c = lane & 7;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double v = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < r; ++k) v = fma(-B[r * SLD + k], x[k], v);   // x[k] = 0 for k < c
-            x[r] = (r >= c) ? v / B[r * SLD + r] : 0.0;
-        }
-        __syncwarp();
-        if (lane < 8) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) B[r * SLD + c] = x[r];
-        }
+    // base: copy the inverted diagonal blocks in (zero strict upper part)
+    for (int e = tid; e < (np >> 3) * 64; e += nt) {
+        const int blk = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        S[(blk * 8 + r) * SLD + blk * 8 + c] = dinv[blk * 8 * DLD + r * DLD + c];
     }
     __syncthreads();
     for (int b = 8; b < np; b <<= 1) {

@@ -137,52 +137,8 @@ int build_dev_kernel(gpb_handle* h, const double* theta, DevKernel* out) {
     for (int p = 0; p < s.n_params; ++p)
         if (!(theta[p] == theta[p])) return set_error(h, -2, "theta[%d] is NaN", p);
     memset(out, 0, sizeof(DevKernel));
-    out->n_dims = s.n_dims; out->n_params = s.n_params;
-    out->n_groups = s.n_groups; out->n_leaves = s.n_leaves; out->n_terms = s.n_terms;
-    for (int g = 0; g < s.n_groups; ++g) {
-        const gpb_group& G = s.groups[g];
-        DevGroup& d = out->groups[g];
-        d.kind = G.kind; d.ard_index = G.ard_index; d.period_index = G.period_index;
-        d.inv_period = (G.period_index >= 0) ? 1.0 / theta[G.period_index] : 0.0;
-        int k = 0;
-        for (int dim = 0; dim < GPB_MAX_DIMS; ++dim) {
-            d.w[dim] = 0.0; d.inv_ls[dim] = 0.0; d.ard_slot[dim] = 0;
-            if (dim < s.n_dims && ((G.dim_mask >> dim) & 1u)) {
-                if (G.ard_index >= 0) {
-                    const double l = theta[G.ard_index + k];
-                    if (!(l > 0.0)) return set_error(h, -2, "ARD lengthscale theta[%d]=%g must be > 0", G.ard_index + k, l);
-                    d.w[dim] = (G.kind == GPB_GROUP_PERIODIC_ABS) ? 1.0 / l : 1.0 / (l * l);
-                    d.inv_ls[dim] = 1.0 / l;
-                    d.ard_slot[dim] = k;
-                } else {
-                    d.w[dim] = 1.0;
-                }
-                ++k;
-            }
-        }
-    }
-    for (int l = 0; l < s.n_leaves; ++l) {
-        const gpb_leaf& L = s.leaves[l];
-        DevLeaf& d = out->leaves[l];
-        d.kind = L.kind; d.group = L.group;
-        d.var_index = L.var_index; d.ls_index = L.ls_index; d.alpha_index = L.alpha_index;
-        d.arg_is_r = (s.groups[L.group].kind == GPB_GROUP_PERIODIC_ABS) ? 1 : 0;
-        d.variance = theta[L.var_index];
-        d.alpha = (L.alpha_index >= 0) ? theta[L.alpha_index] : 1.0;
-        if (L.ls_index >= 0) {
-            const double ls = theta[L.ls_index];
-            if (!(ls > 0.0)) return set_error(h, -2, "lengthscale theta[%d]=%g must be > 0", L.ls_index, ls);
-            d.inv_ls = 1.0 / ls;
-            d.scale = d.arg_is_r ? 1.0 / ls : 1.0 / (ls * ls);
-        } else {
-            d.inv_ls = 0.0;
-            d.scale = 1.0;
-        }
-    }
-    for (int t = 0; t < s.n_terms; ++t) {
-        out->terms[t].n_factors = s.terms[t].n_factors;
-        for (int f = 0; f < GPB_MAX_FACTORS; ++f) out->terms[t].leaf[f] = s.terms[t].leaf[f];
-    }
+    const int bad = build_dev_kernel_core(s, theta, out);
+    if (bad) return set_error(h, -2, "lengthscale theta[%d]=%g must be > 0", bad - 1, theta[bad - 1]);
     return 0;
 }
 
@@ -387,6 +343,29 @@ int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_varianc
     GPB_ENTER(h);
     if (!h_theta || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "predict_f: null pointer");
     return gpr_predict_f(h, h_theta, noise_variance, d_Xs, Ns, d_mean, d_var);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gpb_batched_lml_grad(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                         const double* d_noise, int64_t B, int64_t N, int D, double* d_out, int32_t* d_info,
+                         int want_grad) {
+    GPB_ENTER(h);
+    if (!d_X || !d_Yc || !d_theta || !d_noise || !d_out || !d_info) return set_error(h, -2, "batched_lml_grad: null pointer");
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, B, N, D, want_grad ? 1 : 0, d_out, d_info, nullptr, 0, nullptr,
+                          nullptr);
+}
+
+int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                          const double* d_noise, int64_t B, int64_t N, int D, const double* d_Xs, int64_t Ns,
+                          double* d_mean, double* d_var, int32_t* d_info) {
+    GPB_ENTER(h);
+    if (!d_X || !d_Yc || !d_theta || !d_noise || !d_Xs || !d_mean || !d_var || !d_info)
+        return set_error(h, -2, "batched_predict_f: null pointer");
+    if (Ns <= 0) return 0;
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, B, N, D, 2, nullptr, d_info, d_Xs, Ns, d_mean, d_var);
 }
 
 }  // extern "C"

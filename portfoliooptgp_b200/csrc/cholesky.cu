@@ -21,7 +21,7 @@ namespace gpb {
 
 constexpr int NB = 128;
 constexpr int LEAF_THREADS = 512;
-constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + 16) * sizeof(double);
+constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + DINV_DOUBLES + 16) * sizeof(double);
 
 // One CTA: L = chol(A_blk) in place, W_blk = L^-1, logdiag[blk] = sum log L_ii, info = first bad pivot.
 // The block lives in shared memory (stride SLD); factorisation and inverse run on DMMA tiles
@@ -32,8 +32,8 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* T = sm + NB * SLD;
-    double* rdiag = T + 64 * TLD;
-    int* fail = reinterpret_cast<int*>(rdiag + 8);
+    double* dinv = T + 64 * TLD;
+    int* fail = reinterpret_cast<int*>(dinv + DINV_DOUBLES);
     const int tid = threadIdx.x;
     const int np = (n + 7) & ~7;
     for (int idx = tid; idx < np * NB; idx += LEAF_THREADS) {
@@ -45,7 +45,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
         S[i * SLD + j] = v;
     }
     __syncthreads();
-    block_potrf_lower(S, np, fail, rdiag);
+    block_potrf_lower(S, np, fail, dinv);
     if (tid == 0 && *fail != 0) atomicCAS(info, 0, offset + *fail);
     for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
@@ -60,7 +60,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
         if (tid == 0) logdiag[offset / NB] = s;
     }
     __syncthreads();
-    block_trtri_lower_inplace(S, np, T);
+    block_trtri_lower_inplace(S, np, T, dinv);
     for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
         if (j < n) W[(int64_t)i * ldw + j] = S[i * SLD + j];

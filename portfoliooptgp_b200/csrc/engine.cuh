@@ -109,4 +109,9 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
 int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double* d_Xs, int64_t Ns, double* d_mean,
                   double* d_var);
 
+// ---- batched.cu: one GP per CTA.  mode 0 = LML, 1 = LML + gradient, 2 = predict_f
+int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta, const double* d_noise,
+                   int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int64_t Ns,
+                   double* d_mean, double* d_var);
+
 }  // namespace gpb

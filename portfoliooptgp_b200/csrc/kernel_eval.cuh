@@ -55,6 +55,60 @@ struct DevKernel {
     DevTerm terms[GPB_MAX_TERMS];
 };
 
+// ---- spec + theta -> DevKernel (host and device: the batched path builds one per GP in shared memory) --
+// Returns 0, or 1 + the theta index of a non-positive lengthscale.
+__host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, const double* theta, DevKernel* out) {
+    int bad = 0;
+    out->n_dims = s.n_dims; out->n_params = s.n_params;
+    out->n_groups = s.n_groups; out->n_leaves = s.n_leaves; out->n_terms = s.n_terms;
+    out->pad_ = 0;
+    for (int g = 0; g < s.n_groups; ++g) {
+        const gpb_group& G = s.groups[g];
+        DevGroup& d = out->groups[g];
+        d.kind = G.kind; d.ard_index = G.ard_index; d.period_index = G.period_index; d.pad_ = 0;
+        d.inv_period = (G.period_index >= 0) ? 1.0 / theta[G.period_index] : 0.0;
+        int k = 0;
+        for (int dim = 0; dim < GPB_MAX_DIMS; ++dim) {
+            d.w[dim] = 0.0; d.inv_ls[dim] = 0.0; d.ard_slot[dim] = 0;
+            if (dim < s.n_dims && ((G.dim_mask >> dim) & 1u)) {
+                if (G.ard_index >= 0) {
+                    const double l = theta[G.ard_index + k];
+                    if (!(l > 0.0) && !bad) bad = 1 + G.ard_index + k;
+                    d.w[dim] = (G.kind == GPB_GROUP_PERIODIC_ABS) ? 1.0 / l : 1.0 / (l * l);
+                    d.inv_ls[dim] = 1.0 / l;
+                    d.ard_slot[dim] = k;
+                } else {
+                    d.w[dim] = 1.0;
+                }
+                ++k;
+            }
+        }
+    }
+    for (int l = 0; l < s.n_leaves; ++l) {
+        const gpb_leaf& L = s.leaves[l];
+        DevLeaf& d = out->leaves[l];
+        d.kind = L.kind; d.group = L.group;
+        d.var_index = L.var_index; d.ls_index = L.ls_index; d.alpha_index = L.alpha_index;
+        d.arg_is_r = (s.groups[L.group].kind == GPB_GROUP_PERIODIC_ABS) ? 1 : 0;
+        d.variance = theta[L.var_index];
+        d.alpha = (L.alpha_index >= 0) ? theta[L.alpha_index] : 1.0;
+        if (L.ls_index >= 0) {
+            const double ls = theta[L.ls_index];
+            if (!(ls > 0.0) && !bad) bad = 1 + L.ls_index;
+            d.inv_ls = 1.0 / ls;
+            d.scale = d.arg_is_r ? 1.0 / ls : 1.0 / (ls * ls);
+        } else {
+            d.inv_ls = 0.0;
+            d.scale = 1.0;
+        }
+    }
+    for (int t = 0; t < s.n_terms; ++t) {
+        out->terms[t].n_factors = s.terms[t].n_factors;
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) out->terms[t].leaf[f] = s.terms[t].leaf[f];
+    }
+    return bad;
+}
+
 // ---- group value -------------------------------------------------------------------------------
 // s = reduction over active dims; when GRAD also returns ds/dperiod.
 template <int DP, bool GRAD>

@@ -1,0 +1,86 @@
+"""CPU: lock-step L-BFGS-B reproduces SciPy's iterates; sharding + gather over gloo (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.optimize
+
+from portfoliooptgp_b200.batched import gather_results, lockstep_lbfgsb, shard_range
+
+
+def _rosen_family(a):
+    def f(x):
+        return float(np.sum(a * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+
+    def g(x):
+        out = np.zeros_like(x)
+        out[:-1] += -4 * a * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        out[1:] += 2 * a * (x[1:] - x[:-1] ** 2)
+        return out
+    return f, g
+
+
+def test_lockstep_matches_scipy_iterates():
+    rng = np.random.default_rng(0)
+    B, n = 7, 5
+    coeffs = rng.uniform(1.0, 100.0, size=B)
+    X0 = rng.uniform(-1.5, 1.5, size=(B, n))
+    funs = [_rosen_family(a) for a in coeffs]
+    calls = []
+
+    def fun_batch(X, idx):
+        calls.append(len(idx))
+        f = np.array([funs[b][0](x) for x, b in zip(X, idx)])
+        g = np.stack([funs[b][1](x) for x, b in zip(X, idx)])
+        return f, g
+
+    res = lockstep_lbfgsb(fun_batch, X0, maxiter=60)
+    for b in range(B):
+        ref = scipy.optimize.minimize(lambda x: (funs[b][0](x), funs[b][1](x)), X0[b], jac=True, method="L-BFGS-B",
+                                      options=dict(maxiter=60))
+        assert res[b].nit == ref.nit and res[b].nfev == ref.nfev
+        assert np.array_equal(res[b].x, ref.x)          # bit-identical iterates
+        assert res[b].fun == ref.fun and res[b].status == ref.status
+    assert calls[0] == B and min(calls) >= 1 and len(calls) < sum(r.nfev for r in res)  # batched rounds
+
+
+def test_shard_range_partitions():
+    for total, world in [(5120, 8), (5120, 3), (7, 8), (10, 4)]:
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_range(5120, 3, 8) == (1920, 2560)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    total = 11
+    lo, hi = shard_range(total, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.tensor([[1.0, 10.0, 100.0]], dtype=torch.float64)
+    full = gather_results(local, total)
+    q.put((rank, full.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gather_results_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(11, dtype=np.float64)[:, None] * np.array([[1.0, 10.0, 100.0]])
+    for _, full in outs:
+        assert np.array_equal(full, want)

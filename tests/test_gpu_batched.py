@@ -1,0 +1,87 @@
+"""GPU parity: one-GP-per-CTA batched path vs the CPU oracle and vs the single-GP path (config C3
+shape: N = 128, D = 8, plus ragged sizes N = 63, 67 of the reference's real windows)."""
+import numpy as np
+import pytest
+
+from oracle import gpflow_oracle as O
+from tests.helpers import make_multi_input, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _direct_form():
+    O.set_distance_form("direct")
+    yield
+    O.set_distance_form("gram")
+
+
+def _windows(seed, B, N, D):
+    X, Y = make_multi_input(seed, N + B - 1, D)
+    Xb = np.stack([X[i:i + N] for i in range(B)])
+    Yb = np.stack([Y[i:i + N, 0] for i in range(B)])
+    return Xb, Yb
+
+
+def _kernels(gp, D):
+    K = gp.kernels
+    return {
+        "exp*exp": K.Exponential(active_dims=slice(0, D - 1), lengthscales=1.3) * K.Exponential(active_dims=slice(D - 1, D), variance=0.8),
+        "se+m52+lin": K.SquaredExponential(lengthscales=1.4) + K.Matern52(variance=0.6, lengthscales=2.0) + K.Linear(variance=0.3),
+        "per": K.Matern32(lengthscales=1.5) + K.Periodic(K.SquaredExponential(active_dims=[D - 1]), period=1.3),
+    }
+
+
+@pytest.mark.parametrize("N,D", [(128, 8), (63, 7), (67, 3), (5, 1)])
+def test_batched_lml_grad_matches_oracle(gp, N, D):
+    B = 6
+    Xb, Yb = _windows(3, B, N, D)
+    noise = np.array([1e-2, 1e-1, 1.0, 1e-2, 3e-2, 0.5])
+    for name, k in _kernels(gp, D).items():
+        m = gp.BatchedGPR(Xb, Yb, k, noise_variance=noise)
+        # give every GP its own hyper-parameters
+        rng = np.random.default_rng(1)
+        m.theta = m.theta * rng.uniform(0.7, 1.4, size=m.theta.shape)
+        lml, gth, gnz, info = m.lml_and_grads()
+        assert np.all(info == 0)
+        ko = to_oracle(k)
+        for b in range(B):
+            O.set_theta(ko, m.theta[b])
+            l0, g0, n0 = O.gpr_lml_and_grad(ko, Xb[b], Yb[b][:, None], noise[b])
+            assert abs(lml[b] - l0) <= 1e-9 * abs(l0), (name, b)
+            assert np.max(np.abs(gth[b] - g0)) <= 1e-7 * max(1.0, np.max(np.abs(g0))), (name, b)
+            assert abs(gnz[b] - n0) <= 1e-7 * max(1.0, abs(n0)), (name, b)
+
+
+def test_batched_predict_matches_oracle(gp):
+    B, N, D, Ns = 5, 128, 8, 3
+    Xb, Yb = _windows(4, B, N, D)
+    Xs = np.stack([make_multi_input(40 + b, Ns, D)[0] for b in range(B)])
+    k = _kernels(gp, D)["exp*exp"]
+    m = gp.BatchedGPR(Xb, Yb, k, noise_variance=1e-2)
+    mean, var = m.predict_f(Xs)
+    ko = to_oracle(k)
+    for b in range(B):
+        m0, v0 = O.gpr_predict_f(ko, Xb[b], Yb[b][:, None], 1e-2, Xs[b])
+        assert np.max(np.abs(mean[b].cpu().numpy() - m0[:, 0])) <= 1e-9 * max(1.0, np.max(np.abs(m0)))
+        assert np.max(np.abs(var[b].cpu().numpy() - v0[:, 0])) <= 1e-9
+
+
+def test_batched_fit_equals_per_gp_scipy_fit(gp):
+    """Lock-step fit of B GPs == B separate Scipy().minimize fits of single GPR models
+    (reference models/model_trainer.py:26-48: restarts with trainable noise)."""
+    B, N, D = 4, 64, 3
+    Xb, Yb = _windows(5, 1, N, D)
+    Xb = np.repeat(Xb, B, axis=0); Yb = np.repeat(Yb, B, axis=0)
+    starts = np.array([1e-5, 1e-3, 1e-1, 1.0])
+    k = gp.kernels.SquaredExponential() + gp.kernels.Linear()
+    m = gp.BatchedGPR(Xb, Yb, k, noise_variance=starts, train_noise=True)
+    res = m.fit(maxiter=40)
+    for b in range(B):
+        kb = gp.kernels.SquaredExponential() + gp.kernels.Linear()
+        single = gp.models.GPR((Xb[b], Yb[b][:, None]), kernel=kb, noise_variance=starts[b])
+        gp.set_trainable(single.likelihood, True)
+        r = gp.optimizers.Scipy().minimize(single.training_loss, single.trainable_variables, options=dict(maxiter=40))
+        assert r.nit == res[b].nit
+        assert abs(r.fun - res[b].fun) <= 1e-6 * max(1.0, abs(r.fun))
+        assert np.max(np.abs(r.x - res[b].x)) < 1e-5
