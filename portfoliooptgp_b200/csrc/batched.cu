@@ -77,10 +77,10 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
     // ---- assembly: 8x8 tiles of the lower triangle, fragment layout of the DMMA C tile
     const int nt8 = np >> 3;
     {
-        int idx = 0;
-        for (int ti = 0; ti < nt8; ++ti) {
-            for (int tj = 0; tj <= ti; ++tj, ++idx) {
-                if (idx % BW != warp) continue;
+        for (int t = warp; t < nt8 * (nt8 + 1) / 2; t += BW) {
+            {
+                int ti, tj;
+                tri_tile(t, ti, tj);
                 const int i = ti * 8 + g, j0 = tj * 8 + 2 * q;
                 double xi[DP], xj[DP];
 #pragma unroll
@@ -183,10 +183,10 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
         // ---- gradient: K^-1 tile = sum_{k >= ti*8} W[k, ti-blk]^T W[k, tj-blk] on DMMA, consumed in place
         double acc[GPB_MAX_PARAMS + 1];
         for (int p = 0; p <= P; ++p) acc[p] = 0.0;
-        int idx = 0;
-        for (int ti = 0; ti < nt8; ++ti) {
-            for (int tj = 0; tj <= ti; ++tj, ++idx) {
-                if (idx % BW != warp) continue;
+        for (int t = warp; t < nt8 * (nt8 + 1) / 2; t += BW) {
+            {
+                int ti, tj;
+                tri_tile(t, ti, tj);
                 double c0 = 0.0, c1 = 0.0;
                 const double* Wk = S + (ti * 8) * SLD;
                 warp_tile_mma(c0, c1, Wk + ti * 8, 1, SLD, Wk + tj * 8, SLD, 1, np - ti * 8, 1.0);

@@ -28,6 +28,16 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// linear index t = ti (ti + 1) / 2 + tj  ->  (ti, tj), 0 <= tj <= ti  (small t: float sqrt is exact enough,
+// one correction step each way)
+__device__ __forceinline__ void tri_tile(int t, int& ti, int& tj) {
+    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    if ((r + 1) * (r + 2) / 2 <= t) ++r;
+    if (r * (r + 1) / 2 > t) --r;
+    ti = r;
+    tj = t - r * (r + 1) / 2;
+}
+
 // acc (8x8 tile, DMMA C-fragment: thread holds C[g][2q], C[g][2q+1]) += sign * A[8 x klen] * B[klen x 8]
 //   A(m, k) at A[m * sam + k * sak],  B(k, n) at B[k * sbk + n * sbn];  klen multiple of 4.
 __device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const double* A, int sam, int sak, const double* B,
@@ -124,17 +134,16 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
             }
             __syncthreads();
             // (c) trailing update, 8x8 tiles (ti >= tj) of the trailing matrix: C -= P_ti P_tj^T
-            int idx = 0;
-            for (int ti = 0; ti < mt; ++ti) {
-                for (int tj = 0; tj <= ti; ++tj, ++idx) {
-                    if (idx % nwarps != warp) continue;
-                    double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
-                    double2 cc = *reinterpret_cast<double2*>(C);
-                    const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
-                    const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
-                    warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
-                    *reinterpret_cast<double2*>(C) = cc;
-                }
+            const int ntiles = mt * (mt + 1) / 2;
+            for (int t = warp; t < ntiles; t += nwarps) {
+                int ti, tj;
+                tri_tile(t, ti, tj);
+                double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
+                double2 cc = *reinterpret_cast<double2*>(C);
+                const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
+                const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
+                warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
+                *reinterpret_cast<double2*>(C) = cc;
             }
             __syncthreads();
         }

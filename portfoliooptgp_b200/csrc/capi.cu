@@ -176,9 +176,11 @@ int gpb_create(gpb_handle** out, int device) {
             return -13;  // built for sm_100a only
         }
     }
-    cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming);
+    for (int d = 0; d < gpb_handle::MAX_DEPTH; ++d) {
+        cudaStreamCreateWithFlags(&h->side[d], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_fork[d], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_join[d], cudaEventDisableTiming);
+    }
     *out = h;
     return 0;
 }
@@ -191,9 +193,11 @@ int gpb_destroy(gpb_handle* h) {
         if (h->buf[i]) cudaFree(h->buf[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
-    if (h->side_stream) cudaStreamDestroy(h->side_stream);
-    if (h->ev_a) cudaEventDestroy(h->ev_a);
-    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    for (int d = 0; d < gpb_handle::MAX_DEPTH; ++d) {
+        if (h->side[d]) cudaStreamDestroy(h->side[d]);
+        if (h->ev_fork[d]) cudaEventDestroy(h->ev_fork[d]);
+        if (h->ev_join[d]) cudaEventDestroy(h->ev_join[d]);
+    }
     delete h;
     return 0;
 }

@@ -86,10 +86,10 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
 // A, W: full matrices; factor the diagonal block [o, o+n).  keepL: additionally leave L21 in A21
 // (needs U scratch of n2 x n1 doubles).
 static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
-                          int* info, bool keepL, double* scratchU) {
+                          int* info, bool keepL, double* scratchU, int depth) {
     if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info);
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1, o2 = o + n1;
-    int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU);
+    int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1);
     if (rc) return rc;
     double* A21 = A + (int64_t)o2 * lda + o;
     double* A22 = A + (int64_t)o2 * lda + o2;
@@ -102,6 +102,14 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
     g.transa = 0; g.transb = 1; g.M = n2; g.N = n1; g.K = n1;
     g.A = A21; g.lda = lda; g.B = W11; g.ldb = ldw; g.C = W21; g.ldc = ldw; g.b_upper = 1;
     if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    // fork point: everything that only needs T (and W11) may start now
+    const bool fork = (depth < gpb_handle::MAX_DEPTH) && h->side[depth] && n2 >= 2 * NB;
+    cudaStream_t us = fork ? h->side[depth] : h->stream;
+    if (fork) {
+        cudaError_t e = cudaEventRecord(h->ev_fork[depth], h->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(us, h->ev_fork[depth], 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "fork U stream");
+    }
     // A22 -= T T^T (lower tiles)
     g = GemmArgs();
     g.transa = 0; g.transb = 1; g.M = n2; g.N = n2; g.K = n1; g.alpha = -1.0; g.beta = 1.0;
@@ -117,13 +125,23 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
         U = scratchU;
         ldu = n1;
     }
-    // U = T W11 (W11 lower: k >= j)
+    // U = T W11 (W11 lower: k >= j).  Off the critical path until W21 below: forked onto this depth's
+    // side stream so that it fills the SMs left idle by the latency-bound bottom of the A22 subtree.
     g = GemmArgs();
     g.transa = 0; g.transb = 0; g.M = n2; g.N = n1; g.K = n1;
     g.A = W21; g.lda = ldw; g.B = W11; g.ldb = ldw; g.C = U; g.ldc = ldu; g.b_lower = 1;
-    if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    if ((rc = factor_inv_rec(h, A, lda, W, ldw, o2, n2, logdiag, info, keepL, keepL ? scratchU + (int64_t)n2 * n1 : scratchU)))
+    if ((rc = launch_gemm(h, g, us))) return rc;
+    if (fork) {
+        cudaError_t e = cudaEventRecord(h->ev_join[depth], us);
+        if (e != cudaSuccess) return check_cuda(h, e, "record U join");
+    }
+    if ((rc = factor_inv_rec(h, A, lda, W, ldw, o2, n2, logdiag, info, keepL, keepL ? scratchU + (int64_t)n2 * n1 : scratchU,
+                             depth + 1)))
         return rc;
+    if (fork) {
+        cudaError_t e = cudaStreamWaitEvent(h->stream, h->ev_join[depth], 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "join U stream");
+    }
     // W21 = -W22 U (W22 lower: k <= i)
     g = GemmArgs();
     g.transa = 0; g.transb = 0; g.M = n2; g.N = n1; g.K = n2; g.alpha = -1.0;
@@ -152,7 +170,7 @@ int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, in
     }
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) return check_cuda(h, e, "memset info");
-    return factor_inv_rec(h, A, lda, W, ldw, 0, (int)N, logdiag, d_info, keepL, scratch);
+    return factor_inv_rec(h, A, lda, W, ldw, 0, (int)N, logdiag, d_info, keepL, scratch, 0);
 }
 
 int lauum_lower(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo) {

@@ -12,8 +12,11 @@
 struct gpb_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side_stream = nullptr;  // look-ahead panel work
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // fork/join streams, one per recursion depth of the blocked factorisation: products that are off
+    // the critical path (U = L21 W11) run beside the trailing update and the A22 subtree
+    static constexpr int MAX_DEPTH = 10;
+    cudaStream_t side[MAX_DEPTH] = {};
+    cudaEvent_t ev_fork[MAX_DEPTH] = {}, ev_join[MAX_DEPTH] = {};
     std::string err;
     int64_t launches = 0;
     int sm_count = 148;

@@ -38,6 +38,8 @@ def test_batched_lml_grad_matches_oracle(gp, N, D):
     Xb, Yb = _windows(3, B, N, D)
     noise = np.array([1e-2, 1e-1, 1.0, 1e-2, 3e-2, 0.5])
     for name, k in _kernels(gp, D).items():
+        if D == 1 and name == "exp*exp":
+            continue  # slice(0, D-1) is empty for D = 1
         m = gp.BatchedGPR(Xb, Yb, k, noise_variance=noise)
         # give every GP its own hyper-parameters
         rng = np.random.default_rng(1)

@@ -5,6 +5,99 @@
 #include <cmath>
 #include "../portfoliooptgp_b200/csrc/block_chol.cuh"
 using namespace gpb;
+namespace gpb {
+__device__ __forceinline__ void potrf_timed(double* S, int np, int* fail, double* dinv, long long* tacc) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    if (tid == 0) *fail = 0;
+    __syncthreads();
+    for (int p = 0; p < np; p += 8) {
+        double* M = dinv + (p >> 3) * 8 * DLD;
+        long long ta = clock64();
+        if (warp == 0) {
+            // (a) all 32 lanes hold the whole lower triangle (broadcast loads) and run the same code
+            double a[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) a[r][c] = S[(p + r) * SLD + p + c];
+            double rs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double d = a[j][j];
+                if (!(d > 0.0)) {
+                    if (lane == 0 && *fail == 0) *fail = p + j + 1;
+                    d = 1.0;
+                }
+                rs[j] = rsqrt(d);
+                a[j][j] = d * rs[j];
+#pragma unroll
+                for (int r = j + 1; r < 8; ++r) a[r][j] *= rs[j];
+#pragma unroll
+                for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+                    for (int k = j + 1; k <= r; ++k) a[r][k] = fma(-a[r][j], a[k][j], a[r][k]);
+            }
+            // inverse of the factor: lane c (mod 8) solves column c; 1/L_jj = rs[j]
+            double x[8];
+            const int c = lane & 7;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < r; ++k) v = fma(-a[r][k], x[k], v);
+                x[r] = (r >= c) ? v * rs[r] : 0.0;
+            }
+            // write back: lane r (< 8) writes row r of L (static register indices via the unrolled select)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (lane == r) {
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) S[(p + r) * SLD + p + cc] = (cc <= r) ? a[r][cc] : 0.0;
+                }
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) M[r * DLD + c] = x[r];
+            }
+        }
+        __syncthreads();
+        long long tb = clock64();
+        const int m = np - p - 8;  // rows below the block
+        if (m > 0) {
+            const int mt = m >> 3;
+            // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
+            for (int ti = warp; ti < mt; ti += nwarps) {
+                double* Pt = S + (p + 8 + ti * 8) * SLD + p;
+                double c0 = 0.0, c1 = 0.0;
+                warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+                __syncwarp();
+                *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
+            }
+            __syncthreads();
+            long long tc = clock64();
+            // (c) trailing update, 8x8 tiles (ti >= tj) of the trailing matrix: C -= P_ti P_tj^T
+            int idx = 0;
+            for (int ti = 0; ti < mt; ++ti) {
+                for (int tj = 0; tj <= ti; ++tj, ++idx) {
+                    if (idx % nwarps != warp) continue;
+                    double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
+                    double2 cc = *reinterpret_cast<double2*>(C);
+                    const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
+                    const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
+                    warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
+                    *reinterpret_cast<double2*>(C) = cc;
+                }
+            }
+            __syncthreads();
+            long long td = clock64();
+            if (threadIdx.x == 0) { tacc[0] += tb - ta; tacc[1] += tc - tb; tacc[2] += td - tc; }
+        }
+    }
+}
+
+}
 
 __global__ void __launch_bounds__(512) prof_kernel(const double* A, int n, long long* stamps, double* out) {
     extern __shared__ __align__(16) double sm[];
@@ -14,14 +107,15 @@ __global__ void __launch_bounds__(512) prof_kernel(const double* A, int n, long 
     for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) S[i * SLD + j] = (j <= i) ? A[i * n + j] : 0.0; }
     __syncthreads();
     long long t1 = clock64();
-    block_potrf_lower(S, n, fail, dinv);
+    long long tacc[3] = {0, 0, 0};
+    potrf_timed(S, n, fail, dinv, tacc);
     long long t2 = clock64();
     block_trtri_lower_inplace(S, n, T, dinv);
     long long t3 = clock64();
     for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) out[i * n + j] = S[i * SLD + j]; }
     __syncthreads();
     long long t4 = clock64();
-    if (tid == 0) { stamps[0] = t1 - t0; stamps[1] = t2 - t1; stamps[2] = t3 - t2; stamps[3] = t4 - t3; }
+    if (tid == 0) { stamps[0] = t1 - t0; stamps[1] = t2 - t1; stamps[2] = t3 - t2; stamps[3] = t4 - t3; stamps[4] = tacc[0]; stamps[5] = tacc[1]; stamps[6] = tacc[2]; }
 }
 
 // isolated micro-latencies
@@ -55,8 +149,8 @@ int main() {
     cudaFuncSetAttribute(prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int threads : {256, 512}) {
         for (int rep = 0; rep < 2; ++rep) prof_kernel<<<1, threads, smem>>>(dA, n, dS, dO);
-        long long st[4]; cudaMemcpy(st, dS, 32, cudaMemcpyDeviceToHost);
-        printf("threads %d cycles: load %lld potrf %lld trtri %lld store %lld (err %s)\n", threads, st[0], st[1], st[2], st[3], cudaGetErrorString(cudaGetLastError()));
+        long long st[7]; cudaMemcpy(st, dS, 56, cudaMemcpyDeviceToHost);
+        printf("threads %d cycles: load %lld potrf %lld [a %lld b %lld c %lld] trtri %lld store %lld (err %s)\n", threads, st[0], st[1], st[4], st[5], st[6], st[2], st[3], cudaGetErrorString(cudaGetLastError()));
     }
     lat_kernel<<<1, 32>>>(dS, 1.3);
     long long l[7]; cudaMemcpy(l, dS, 56, cudaMemcpyDeviceToHost);
