@@ -160,8 +160,13 @@ grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restric
     __syncthreads();
 
     const int P = kp.n_params;
+    const bool fast = grad_fast_ok(kp);   // register accumulators (every reference kernel) vs generic path
+    GradAcc A;
+    A.zero();
+    double tr = 0.0;
     double acc[GPB_MAX_PARAMS + 1];
-    for (int p = 0; p <= P; ++p) acc[p] = 0.0;
+    if (!fast)
+        for (int p = 0; p <= P; ++p) acc[p] = 0.0;
 
     const int tx = tid & 31, ty = tid >> 5;
     const int c0 = 2 * tx;
@@ -194,22 +199,33 @@ grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restric
         const double ai = al_i[r];
         {
             double w = ai * al_j[c0] - k0;
-            if (gj == gi) { acc[P] += w; } else { w *= 2.0; }
-            kernel_value_grad<DP>(kp, xi, xj0, w, acc);
+            if (gj == gi) { tr += w; } else { w *= 2.0; }
+            if (fast) kernel_value_grad_fast<DP>(kp, xi, xj0, w, A);
+            else kernel_value_grad<DP>(kp, xi, xj0, w, acc);
         }
         if (gj + 1 <= gi) {
             double w = ai * al_j[c0 + 1] - k1;
-            if (gj + 1 == gi) { acc[P] += w; } else { w *= 2.0; }
-            kernel_value_grad<DP>(kp, xi, xj1, w, acc);
+            if (gj + 1 == gi) { tr += w; } else { w *= 2.0; }
+            if (fast) kernel_value_grad_fast<DP>(kp, xi, xj1, w, A);
+            else kernel_value_grad<DP>(kp, xi, xj1, w, acc);
         }
     }
     // block reduction in a fixed order (deterministic): warp shuffle, then warp 0 sums the 8 rows
-    for (int p = 0; p <= P; ++p) {
-        double v = acc[p];
+    if (fast) {
+        for (int p = tx; p <= P; p += 32) red[ty][p] = 0.0;
+        __syncwarp();
+        grad_flush(kp, A, red[ty]);
+    } else {
+        for (int p = 0; p < P; ++p) {
+            double v = acc[p];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (tx == 0) red[ty][p] = v;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (tx == 0) red[ty][p] = v;
+        }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tr += __shfl_down_sync(0xffffffffu, tr, o);
+    if (tx == 0) red[ty][P] = tr;
     __syncthreads();
     if (tid <= P) {
         double v = 0.0;

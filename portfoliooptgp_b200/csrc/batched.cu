@@ -181,8 +181,13 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
     double* o = out + (size_t)b * (2 + P);
     if (mode == 1) {
         // ---- gradient: K^-1 tile = sum_{k >= ti*8} W[k, ti-blk]^T W[k, tj-blk] on DMMA, consumed in place
+        const bool fast = grad_fast_ok(kp);
+        GradAcc A;
+        A.zero();
+        double tr = 0.0;
         double acc[GPB_MAX_PARAMS + 1];
-        for (int p = 0; p <= P; ++p) acc[p] = 0.0;
+        if (!fast)
+            for (int p = 0; p <= P; ++p) acc[p] = 0.0;
         for (int t = warp; t < nt8 * (nt8 + 1) / 2; t += BW) {
             {
                 int ti, tj;
@@ -201,22 +206,33 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
                         const int j = j0 + c;
                         if (j <= i) {
                             double w = ai * als[j] - (c == 0 ? c0 : c1);
-                            if (j == i) acc[P] += w; else w *= 2.0;
+                            if (j == i) tr += w; else w *= 2.0;
 #pragma unroll
                             for (int d = 0; d < DP; ++d) xj[d] = xs[j * DP + d];
-                            kernel_value_grad<DP>(kp, xi, xj, w, acc);
+                            if (fast) kernel_value_grad_fast<DP>(kp, xi, xj, w, A);
+                            else kernel_value_grad<DP>(kp, xi, xj, w, acc);
                         }
                     }
                 }
                 __syncwarp();
             }
         }
-        for (int p = 0; p <= P; ++p) {
-            double v = acc[p];
+        double* redw = red + warp * (GPB_MAX_PARAMS + 2);
+        if (fast) {
+            for (int p = lane; p <= P; p += 32) redw[p] = 0.0;
+            __syncwarp();
+            grad_flush(kp, A, redw);
+        } else {
+            for (int p = 0; p < P; ++p) {
+                double v = acc[p];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) red[warp * (GPB_MAX_PARAMS + 2) + p] = v;
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) redw[p] = v;
+            }
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tr += __shfl_down_sync(0xffffffffu, tr, off);
+        if (lane == 0) redw[P] = tr;
         __syncthreads();
         if (tid <= P) {
             double v = 0.0;

@@ -17,6 +17,8 @@
 //   transb = 1: B is [N,K] (k contiguous)      transb = 0: B is [K,N] (n contiguous)
 // Triangular structure is exploited at tile granularity through per-tile k ranges; diagonal blocks
 // of triangular operands must carry explicit zeros in their strict upper part (engine convention).
+#include <stdlib.h>
+
 #include "engine.cuh"
 
 namespace gpb {
@@ -238,8 +240,26 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     return check_cuda(h, cudaGetLastError(), "dgemm_kernel launch");
 }
 
+static int gemm_cfg_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPB_GEMM_CFG");   // tuning knob for tools/gemm_bench.py; 0 / unset = automatic
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <bool AKC, bool BKC>
 static int launch_layout(gpb_handle* h, const GemmParams& p, cudaStream_t stream) {
+    switch (gemm_cfg_override()) {
+        case 1: return launch_cfg<128, 128, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
+        case 2: return launch_cfg<128, 64, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
+        case 3: return launch_cfg<128, 128, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
+        case 4: return launch_cfg<128, 64, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
+        case 5: return launch_cfg<128, 128, 16, 32, 64, 4, AKC, BKC>(h, p, stream);
+        case 6: return launch_cfg<64, 128, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
+        default: break;
+    }
     // Large tiles when they fill the machine, small tiles otherwise (more CTAs for short problems).
     const int64_t big_tiles = p.tri ? ((int64_t)((p.M + 127) / 128) * ((p.M + 127) / 128 + 1) / 2)
                                     : ((int64_t)((p.M + 127) / 128) * ((p.N + 127) / 128));

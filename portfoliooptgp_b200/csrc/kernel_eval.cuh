@@ -49,7 +49,7 @@ struct DevTerm {
 
 struct DevKernel {
     int n_dims, n_params, n_groups, n_leaves, n_terms;
-    int pad_;
+    int has_ard;  // any group with per-dimension lengthscales (gradient takes the generic path)
     DevGroup groups[GPB_MAX_GROUPS];
     DevLeaf leaves[GPB_MAX_LEAVES];
     DevTerm terms[GPB_MAX_TERMS];
@@ -61,7 +61,7 @@ __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, c
     int bad = 0;
     out->n_dims = s.n_dims; out->n_params = s.n_params;
     out->n_groups = s.n_groups; out->n_leaves = s.n_leaves; out->n_terms = s.n_terms;
-    out->pad_ = 0;
+    out->has_ard = 0;
     for (int g = 0; g < s.n_groups; ++g) {
         const gpb_group& G = s.groups[g];
         DevGroup& d = out->groups[g];
@@ -72,6 +72,7 @@ __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, c
             d.w[dim] = 0.0; d.inv_ls[dim] = 0.0; d.ard_slot[dim] = 0;
             if (dim < s.n_dims && ((G.dim_mask >> dim) & 1u)) {
                 if (G.ard_index >= 0) {
+                    out->has_ard = 1;
                     const double l = theta[G.ard_index + k];
                     if (!(l > 0.0) && !bad) bad = 1 + G.ard_index + k;
                     d.w[dim] = (G.kind == GPB_GROUP_PERIODIC_ABS) ? 1.0 / l : 1.0 / (l * l);
@@ -316,6 +317,116 @@ __device__ __forceinline__ double kernel_value_grad(const DevKernel& kp, const d
         }
     }
     return total;
+}
+
+
+// ---- register-resident gradient path ---------------------------------------------------------------
+// For expressions with <= GRAD_FAST_LEAVES leaves and no ARD group every parameter derivative is
+// accumulated in statically indexed registers (4 slots per leaf: variance, scalar lengthscale, alpha,
+// period) instead of a dynamically indexed per-thread array; the slots are scattered to theta
+// indices once per thread at the end (grad_flush).  Covers every kernel the reference builds.
+constexpr int GRAD_FAST_LEAVES = 4;
+
+struct GradAcc {
+    double var[GRAD_FAST_LEAVES], ls[GRAD_FAST_LEAVES], alpha[GRAD_FAST_LEAVES], period[GRAD_FAST_LEAVES];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int l = 0; l < GRAD_FAST_LEAVES; ++l) var[l] = ls[l] = alpha[l] = period[l] = 0.0;
+    }
+};
+
+__device__ __forceinline__ bool grad_fast_ok(const DevKernel& kp) {
+    return kp.n_leaves <= GRAD_FAST_LEAVES && !kp.has_ard;
+}
+
+__device__ __forceinline__ double sel4(const double (&a)[GRAD_FAST_LEAVES], int id) {
+    double r = a[0];
+#pragma unroll
+    for (int l = 1; l < GRAD_FAST_LEAVES; ++l) r = (id == l) ? a[l] : r;
+    return r;
+}
+
+template <int DP>
+__device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, const double (&xi)[DP],
+                                                         const double (&xj)[DP], double wgt, GradAcc& A) {
+    double v[GRAD_FAST_LEAVES], fval[GRAD_FAST_LEAVES], dls[GRAD_FAST_LEAVES], dal[GRAD_FAST_LEAVES],
+        dper[GRAD_FAST_LEAVES], ladj[GRAD_FAST_LEAVES];
+    double s_prev = 0.0, dsp_prev = 0.0;
+    int g_prev = -1;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        v[l] = 1.0; fval[l] = dls[l] = dal[l] = dper[l] = 0.0; ladj[l] = 0.0;
+        if (l < kp.n_leaves) {
+            const DevLeaf& lf = kp.leaves[l];
+            if (lf.group != g_prev) {
+                s_prev = group_value<DP, true>(kp.groups[lf.group], xi, xj, dsp_prev);
+                g_prev = lf.group;
+            }
+            const LeafOut lo = leaf_value<true>(lf, s_prev);
+            v[l] = lo.v;
+            fval[l] = lo.f;
+            dls[l] = lo.dv_du_u * (lf.arg_is_r ? -1.0 : -2.0) * lf.inv_ls;   // inv_ls = 0 without a scalar lengthscale
+            dal[l] = lo.dv_dalpha;
+            dper[l] = lo.dv_ds * dsp_prev;                                   // 0 for non-periodic groups
+        }
+    }
+    double total = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        double fv[GPB_MAX_FACTORS];
+        double prod = 1.0;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            fv[f] = (f < tm.n_factors) ? sel4(v, tm.leaf[f]) : 1.0;
+            prod *= fv[f];
+        }
+        total += prod;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            if (f < tm.n_factors) {
+                double adj = wgt;
+#pragma unroll
+                for (int f2 = 0; f2 < GPB_MAX_FACTORS; ++f2)
+                    if (f2 != f) adj *= fv[f2];
+                const int id = tm.leaf[f];
+#pragma unroll
+                for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? adj : 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        A.var[l] = fma(ladj[l], fval[l], A.var[l]);
+        A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
+        A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
+        A.period[l] = fma(ladj[l], dper[l], A.period[l]);
+    }
+    return total;
+}
+
+// Warp-reduce the register accumulators (fixed shuffle tree) and let lane 0 add them into out[0..P)
+// (a zero-initialised per-warp row, any memory space) at their theta indices, in a fixed order.
+__device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, double* out) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        double a = A.var[l], b = A.ls[l], c = A.alpha[l], d = A.period[l];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+            c += __shfl_down_sync(0xffffffffu, c, o);
+            d += __shfl_down_sync(0xffffffffu, d, o);
+        }
+        if (lane == 0 && l < kp.n_leaves) {
+            const DevLeaf& lf = kp.leaves[l];
+            out[lf.var_index] += a;
+            if (lf.ls_index >= 0) out[lf.ls_index] += b;
+            if (lf.alpha_index >= 0) out[lf.alpha_index] += c;
+            const int pi = kp.groups[lf.group].period_index;
+            if (pi >= 0) out[pi] += d;
+        }
+    }
 }
 
 // k(x, x) on the diagonal (gpflow K_diag): stationary -> variance, Linear -> sum w_d x_d^2.
