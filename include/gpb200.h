@@ -173,6 +173,30 @@ int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, 
                           const double* d_noise, int64_t B, int64_t N, int D, const double* d_Xs,
                           int64_t Ns, double* d_mean, double* d_var, int32_t* d_info);
 
+/* ---- SVGP (north_star subsystem 5) ---------------------------------------------------------------
+ * Replaces gpflow.models.SVGP(kernel, Gaussian, Z, num_data).elbo / training_loss_closure /
+ * predict_f (test_scripts/SVGP.py:515-540): whiten=True, q_diag=False, one latent GP.
+ * All d_* are device pointers: d_Z [M,D], d_qmu [M], d_qsqrt [M, ldq] lower triangular with zeros
+ * above the diagonal, d_Xb [B,D], d_Yb [B].
+ *
+ * gpb_svgp_data_term: minibatch pass.  Writes the flat record d_flat (gpb_svgp_flat_size doubles):
+ *   [0] S = sum_b E_q[log p(y_b|f_b)]  (UNSCALED)   [1] dS/dnoise   [2,2+P) dS/dtheta
+ *   then dS/dZ [M,D], dS/dq_mu [M], dS/dq_sqrt [M,M] (row-major).  Asynchronous.  Data-parallel
+ *   ranks sum their records with ONE all-reduce (NCCL) before gpb_svgp_finish.
+ * gpb_svgp_finish: ELBO = scale * S - KL[q(u)||p(u)]; with apply_grad the record is turned in place
+ *   into d ELBO / d(noise, theta, Z, q_mu, q_sqrt) (KL added once -- SURVEY.md H8).  Synchronises. */
+int64_t gpb_svgp_flat_size(int64_t M, int D, int n_params);
+int gpb_svgp_data_term(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z,
+                       int64_t M, int D, const double* d_qmu, const double* d_qsqrt, int64_t ldq,
+                       const double* d_Xb, const double* d_Yb, int64_t B, double* d_flat, int want_grad);
+int gpb_svgp_finish(gpb_handle* h, double* d_flat, double scale, const double* d_qmu,
+                    const double* d_qsqrt, int64_t ldq, int64_t M, int D, int n_params, int apply_grad,
+                    double* h_elbo, double* h_kl);
+/* SVGP.predict_f(Xnew, full_cov=False): d_mean, d_var [Ns] (mean excludes mean_function). */
+int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, int64_t M, int D,
+                       const double* d_qmu, const double* d_qsqrt, int64_t ldq, const double* d_Xs,
+                       int64_t Ns, double* d_mean, double* d_var);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ and the reference call sites (GPR/model_trainer.py, GPR/predictor.py,
 Multi-Input_GPR/models/model_trainer.py, test_scripts/SVGP.py) run unchanged apart from the
 import and from passing numpy / torch arrays instead of tf tensors.  There is no CPU fallback."""
 from . import config, kernels, likelihoods, mean_functions, models, optimizers, utilities  # noqa: F401
+from . import inducing_variables  # noqa: F401
 from .base import Module, Parameter, set_trainable  # noqa: F401
 from .config import default_float, default_jitter  # noqa: F401
 from ._capi import CholeskyError, EngineError  # noqa: F401

@@ -86,6 +86,10 @@ SIGNATURES = {
     "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
     "gpb_batched_lml_grad": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
     "gpb_batched_predict_f": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
+    "gpb_svgp_flat_size": (_I64, [_I64, _INT, _INT]),
+    "gpb_svgp_data_term": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _P, _I64, _P, _INT]),
+    "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
+    "gpb_svgp_predict_f": (_INT, [_P, _DP, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
 }
 
 
@@ -231,3 +235,27 @@ class Engine:
                           dmean: int, dvar: int, dinfo: int):
         self._check(self._lib.gpb_batched_predict_f(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dXs),
                                                     Ns, _P(dmean), _P(dvar), _P(dinfo)), "gpb_batched_predict_f")
+
+    # -- SVGP ---------------------------------------------------------------------------------------
+    def svgp_flat_size(self, M: int, D: int, P: int) -> int:
+        return int(self._lib.gpb_svgp_flat_size(M, D, P))
+
+    def svgp_data_term(self, theta: np.ndarray, noise: float, dZ: int, M: int, D: int, dqmu: int, dqsqrt: int, ldq: int,
+                       dXb: int, dYb: int, B: int, dflat: int, want_grad: bool = True):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb_svgp_data_term(self._h, _as_dp(theta), float(noise), _P(dZ), M, D, _P(dqmu), _P(dqsqrt),
+                                                 ldq, _P(dXb), _P(dYb), B, _P(dflat), int(bool(want_grad))),
+                    "gpb_svgp_data_term")
+
+    def svgp_finish(self, dflat: int, scale: float, dqmu: int, dqsqrt: int, ldq: int, M: int, D: int, P: int,
+                    apply_grad: bool = True):
+        elbo, kl = C.c_double(), C.c_double()
+        self._check(self._lib.gpb_svgp_finish(self._h, _P(dflat), float(scale), _P(dqmu), _P(dqsqrt), ldq, M, D, P,
+                                              int(bool(apply_grad)), C.byref(elbo), C.byref(kl)), "gpb_svgp_finish")
+        return elbo.value, kl.value
+
+    def svgp_predict_f(self, theta: np.ndarray, dZ: int, M: int, D: int, dqmu: int, dqsqrt: int, ldq: int, dXs: int,
+                       Ns: int, dmean: int, dvar: int):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        self._check(self._lib.gpb_svgp_predict_f(self._h, _as_dp(theta), _P(dZ), M, D, _P(dqmu), _P(dqsqrt), ldq, _P(dXs),
+                                                 Ns, _P(dmean), _P(dvar)), "gpb_svgp_predict_f")

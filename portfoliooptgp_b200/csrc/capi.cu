@@ -373,3 +373,32 @@ int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, 
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int64_t gpb_svgp_flat_size(int64_t M, int D, int n_params) { return 2 + (int64_t)n_params + M * D + M + M * M; }
+
+int gpb_svgp_data_term(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z, int64_t M, int D,
+                       const double* d_qmu, const double* d_qsqrt, int64_t ldq, const double* d_Xb, const double* d_Yb,
+                       int64_t B, double* d_flat, int want_grad) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Z || !d_qmu || !d_qsqrt || !d_Xb || !d_Yb || !d_flat) return set_error(h, -2, "svgp_data_term: null pointer");
+    if (ldq < M) return set_error(h, -2, "svgp_data_term: ldq < M");
+    return svgp_data_term(h, h_theta, noise_variance, d_Z, M, D, d_qmu, d_qsqrt, ldq, d_Xb, d_Yb, B, d_flat, want_grad);
+}
+
+int gpb_svgp_finish(gpb_handle* h, double* d_flat, double scale, const double* d_qmu, const double* d_qsqrt, int64_t ldq,
+                    int64_t M, int D, int n_params, int apply_grad, double* h_elbo, double* h_kl) {
+    GPB_ENTER(h);
+    if (!d_flat || !d_qmu || !d_qsqrt || !h_elbo || !h_kl) return set_error(h, -2, "svgp_finish: null pointer");
+    return svgp_finish(h, d_flat, scale, d_qmu, d_qsqrt, ldq, M, D, n_params, apply_grad, h_elbo, h_kl);
+}
+
+int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, int64_t M, int D, const double* d_qmu,
+                       const double* d_qsqrt, int64_t ldq, const double* d_Xs, int64_t Ns, double* d_mean, double* d_var) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Z || !d_qmu || !d_qsqrt || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "svgp_predict_f: null pointer");
+    return svgp_predict_f(h, h_theta, d_Z, M, D, d_qmu, d_qsqrt, ldq, d_Xs, Ns, d_mean, d_var);
+}
+
+}  // extern "C"

@@ -117,4 +117,13 @@ int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const d
                    int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int64_t Ns,
                    double* d_mean, double* d_var);
 
+// ---- svgp.cu
+int svgp_data_term(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D,
+                   const double* d_qmu, const double* d_Lq, int64_t ldq, const double* d_X, const double* d_y, int64_t B,
+                   double* d_flat, int want_grad);
+int svgp_finish(gpb_handle* h, double* d_flat, double scale, const double* d_qmu, const double* d_Lq, int64_t ldq,
+                int64_t M, int D, int P, int apply_grad, double* h_elbo, double* h_kl);
+int svgp_predict_f(gpb_handle* h, const double* theta, const double* d_Z, int64_t M, int D, const double* d_qmu,
+                   const double* d_Lq, int64_t ldq, const double* d_Xs, int64_t Ns, double* d_mean, double* d_var);
+
 }  // namespace gpb

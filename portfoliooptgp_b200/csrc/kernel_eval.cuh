@@ -404,6 +404,114 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
     return total;
 }
 
+// gx[d] += coef * ds/dx_d for one group (derivative w.r.t. the FIRST argument x)
+template <int DP>
+__device__ __forceinline__ void add_group_dx(const DevGroup& g, const double (&xi)[DP], const double (&xj)[DP],
+                                             double coef, double (&gx)[DP]) {
+    switch (g.kind) {
+        case GPB_GROUP_EUCLID: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) gx[d] = fma(2.0 * coef * g.w[d], xi[d] - xj[d], gx[d]);
+        } break;
+        case GPB_GROUP_DOT: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) gx[d] = fma(coef * g.w[d], xj[d], gx[d]);
+        } break;
+        case GPB_GROUP_PERIODIC_SQ: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                if (g.w[d] != 0.0) {
+                    double sn, cs;
+                    sincospi((xi[d] - xj[d]) * g.inv_period, &sn, &cs);
+                    gx[d] = fma(coef * g.w[d] * 2.0 * sn * cs, M_PI * g.inv_period, gx[d]);
+                }
+            }
+        } break;
+        default: {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                if (g.w[d] != 0.0) {
+                    double sn, cs;
+                    sincospi((xi[d] - xj[d]) * g.inv_period, &sn, &cs);
+                    const double sg = (sn > 0.0) ? 1.0 : ((sn < 0.0) ? -1.0 : 0.0);
+                    gx[d] = fma(coef * g.w[d] * sg * cs, M_PI * g.inv_period, gx[d]);
+                }
+            }
+        } break;
+    }
+}
+
+// As kernel_value_grad_fast, and additionally gx[d] += wgt * dk(x, x')/dx_d (first argument): the
+// inducing-point gradient of the SVGP path (gpflow trains inducing_variable.Z).
+template <int DP>
+__device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, const double (&xi)[DP],
+                                                           const double (&xj)[DP], double wgt, GradAcc& A,
+                                                           double (&gx)[DP]) {
+    double v[GRAD_FAST_LEAVES], fval[GRAD_FAST_LEAVES], dls[GRAD_FAST_LEAVES], dal[GRAD_FAST_LEAVES],
+        dper[GRAD_FAST_LEAVES], dvds[GRAD_FAST_LEAVES], ladj[GRAD_FAST_LEAVES];
+    double s_prev = 0.0, dsp_prev = 0.0;
+    int g_prev = -1;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        v[l] = 1.0; fval[l] = dls[l] = dal[l] = dper[l] = dvds[l] = 0.0; ladj[l] = 0.0;
+        if (l < kp.n_leaves) {
+            const DevLeaf& lf = kp.leaves[l];
+            if (lf.group != g_prev) {
+                s_prev = group_value<DP, true>(kp.groups[lf.group], xi, xj, dsp_prev);
+                g_prev = lf.group;
+            }
+            const LeafOut lo = leaf_value<true>(lf, s_prev);
+            v[l] = lo.v;
+            fval[l] = lo.f;
+            dls[l] = lo.dv_du_u * (lf.arg_is_r ? -1.0 : -2.0) * lf.inv_ls;
+            dal[l] = lo.dv_dalpha;
+            dper[l] = lo.dv_ds * dsp_prev;
+            dvds[l] = lo.dv_ds;
+        }
+    }
+    double total = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        double fv[GPB_MAX_FACTORS];
+        double prod = 1.0;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            fv[f] = (f < tm.n_factors) ? sel4(v, tm.leaf[f]) : 1.0;
+            prod *= fv[f];
+        }
+        total += prod;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            if (f < tm.n_factors) {
+                double adj = wgt;
+#pragma unroll
+                for (int f2 = 0; f2 < GPB_MAX_FACTORS; ++f2)
+                    if (f2 != f) adj *= fv[f2];
+                const int id = tm.leaf[f];
+#pragma unroll
+                for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? adj : 0.0;
+            }
+        }
+    }
+    double cacc = 0.0;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        A.var[l] = fma(ladj[l], fval[l], A.var[l]);
+        A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
+        A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
+        A.period[l] = fma(ladj[l], dper[l], A.period[l]);
+        if (l < kp.n_leaves) {
+            cacc = fma(ladj[l], dvds[l], cacc);
+            const bool last = (l + 1 >= kp.n_leaves) || (kp.leaves[l + 1].group != kp.leaves[l].group);
+            if (last) {
+                add_group_dx<DP>(kp.groups[kp.leaves[l].group], xi, xj, cacc, gx);
+                cacc = 0.0;
+            }
+        }
+    }
+    return total;
+}
+
 // Warp-reduce the register accumulators (fixed shuffle tree) and let lane 0 add them into out[0..P)
 // (a zero-initialised per-warp row, any memory space) at their theta indices, in a fixed order.
 __device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, double* out) {

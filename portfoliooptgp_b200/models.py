@@ -110,6 +110,8 @@ class GPModel(Module):
     def _training_loss(self, data):
         return -self._mll(data)
 
+    # (SVGP overrides training_loss / _training_loss: its objective needs the minibatch)
+
     def _mll(self, data):
         raise NotImplementedError
 
@@ -222,3 +224,157 @@ class GPR(GPModel):
         if not isinstance(self.mean_function, Zero):
             mean = mean + self.mean_function(Xs)
         return _out(mean), _out(out[1][:, None])
+
+
+class InducingPoints(Module):
+    """gpflow.inducing_variables.InducingPoints: Z [M, D], trainable, identity transform."""
+
+    def __init__(self, Z):
+        Z = np.asarray(Z.numpy() if isinstance(Z, Parameter) else ops_to_numpy(Z), dtype=np.float64)
+        if Z.ndim == 1:
+            Z = Z[:, None]
+        self.Z = Parameter(Z, name="Z")
+
+    @property
+    def num_inducing(self) -> int:
+        return int(self.Z.shape[0])
+
+    def __len__(self):
+        return self.num_inducing
+
+
+def ops_to_numpy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class SVGP(GPModel):
+    """Sparse variational GP (gpflow/models/svgp.py) as constructed at test_scripts/SVGP.py:515-521:
+    ``SVGP(kernel, Gaussian(variance), inducing_variable=Z, num_data=N)`` with GPflow's defaults
+    whiten=True, q_diag=False, one latent GP, q_mu = 0, q_sqrt = I.
+
+    elbo(data) = num_data / B * sum_b E_q[log p(y_b | f_b)] - KL[q(u) || p(u)]  (SURVEY.md G13-G14);
+    the data term, its adjoint and the KL run on the device (csrc/svgp.cu)."""
+
+    def __init__(self, kernel: Kernel, likelihood: Gaussian, inducing_variable, *, mean_function=None,
+                 num_latent_gps: int = 1, q_diag: bool = False, q_mu=None, q_sqrt=None, whiten: bool = True,
+                 num_data: Optional[int] = None, device=None):
+        if not isinstance(likelihood, Gaussian):
+            raise NotImplementedError("only the Gaussian likelihood is on the reference path")
+        if num_latent_gps != 1 or q_diag or not whiten:
+            raise NotImplementedError("SVGP supports the reference configuration: one latent GP, q_diag=False, whiten=True")
+        if mean_function is not None and not isinstance(mean_function, Zero):
+            raise NotImplementedError("SVGP mean functions are not on the reference path")
+        super().__init__(kernel, likelihood, mean_function, device)
+        self.inducing_variable = inducing_variable if isinstance(inducing_variable, InducingPoints) else InducingPoints(inducing_variable)
+        M = self.inducing_variable.num_inducing
+        self.num_data = num_data
+        self.whiten = whiten
+        self.q_diag = q_diag
+        self.num_latent_gps = 1
+        self.q_mu = Parameter(np.zeros((M, 1)) if q_mu is None else np.asarray(ops_to_numpy(q_mu), dtype=np.float64).reshape(M, 1),
+                              name="q_mu")
+        qs = np.eye(M)[None] if q_sqrt is None else np.asarray(ops_to_numpy(q_sqrt), dtype=np.float64).reshape(1, M, M)
+        self.q_sqrt = Parameter(qs, transform=triangular(M), name="q_sqrt")
+        self._flat: Optional[torch.Tensor] = None
+
+    def _children(self):
+        for key, val in super()._children():
+            if key not in ("num_data", "whiten", "q_diag", "num_latent_gps"):
+                yield key, val
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _device_params(self):
+        dev = torch.device("cuda", self._device_index)
+        Z = torch.from_numpy(np.ascontiguousarray(self.inducing_variable.Z.numpy())).to(dev)
+        qmu = torch.from_numpy(np.ascontiguousarray(self.q_mu.numpy()[:, 0])).to(dev)
+        Lq = torch.from_numpy(np.ascontiguousarray(np.tril(self.q_sqrt.numpy()[0]))).to(dev)
+        return Z, qmu, Lq
+
+    def _data(self, data):
+        if data is None:
+            raise ValueError("SVGP objectives need data=(X, Y)")
+        X, Y = data
+        Xd = ops.to_device(X, self._device_index, ndim=2)
+        Yd = ops.to_device(Y, self._device_index, ndim=2)
+        if Yd.shape[1] != 1 or Yd.shape[0] != Xd.shape[0]:
+            raise ValueError("Y must be [N, 1] with as many rows as X")
+        return Xd, Yd[:, 0].contiguous()
+
+    def _scale(self, B: int) -> float:
+        return 1.0 if self.num_data is None else float(self.num_data) / float(B)
+
+    def _run(self, data, want_grad: bool):
+        Xd, yd = self._data(data)
+        eng = self._get_engine()
+        Z, qmu, Lq = self._device_params()
+        M, D = Z.shape
+        if Xd.shape[1] != D:
+            raise ValueError(f"X has {Xd.shape[1]} columns, Z has {D}")
+        ck = self._lower_kernel(D)
+        n = eng.svgp_flat_size(M, D, ck.n_params)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=torch.float64, device=Xd.device)
+        noise = float(self.likelihood.variance.numpy())
+        eng.svgp_data_term(ck.theta(), noise, Z.data_ptr(), M, D, qmu.data_ptr(), Lq.data_ptr(), M, Xd.data_ptr(),
+                           yd.data_ptr(), Xd.shape[0], self._flat.data_ptr(), want_grad)
+        elbo, kl = eng.svgp_finish(self._flat.data_ptr(), self._scale(Xd.shape[0]), qmu.data_ptr(), Lq.data_ptr(), M, M, D,
+                                   ck.n_params, want_grad)
+        return elbo, kl, ck, M, D
+
+    # -- GPflow surface --------------------------------------------------------------------------
+    def elbo(self, data):
+        return torch.tensor(self._run(data, False)[0], dtype=torch.float64)
+
+    def maximum_log_likelihood_objective(self, data):
+        return self.elbo(data)
+
+    def prior_kl(self):
+        eng = self._get_engine()
+        Z, qmu, Lq = self._device_params()
+        M, D = Z.shape
+        scratch = torch.zeros(eng.svgp_flat_size(M, D, 1), dtype=torch.float64, device=Z.device)
+        return torch.tensor(eng.svgp_finish(scratch.data_ptr(), 1.0, qmu.data_ptr(), Lq.data_ptr(), M, M, D, 1, False)[1],
+                            dtype=torch.float64)
+
+    def training_loss(self, data):
+        return -self.elbo(data)
+
+    def training_loss_closure(self, data, *, compile: bool = True) -> LossClosure:
+        Xd, yd = self._data(data)
+        return LossClosure(self, (Xd, yd[:, None]))
+
+    def _training_loss(self, data):
+        return -self.elbo(data)
+
+    def _training_loss_and_grads(self, variables: Sequence[Variable], data=None):
+        elbo, kl, ck, M, D = self._run(data, True)
+        flat = self._flat.cpu().numpy()
+        P = ck.n_params
+        by_param = ck.scatter_grad(flat[2:2 + P])
+        pv = self.likelihood.variance
+        by_param[id(pv)] = np.asarray(flat[1]) * pv.transform.forward_grad(pv.unconstrained_variable._value)
+        o = 2 + P
+        by_param[id(self.inducing_variable.Z)] = flat[o:o + M * D].reshape(M, D)
+        o += M * D
+        by_param[id(self.q_mu)] = flat[o:o + M].reshape(M, 1)
+        o += M
+        by_param[id(self.q_sqrt)] = self.q_sqrt.transform.pull_back(flat[o:o + M * M].reshape(1, M, M))
+        return -elbo, self._grads_for(variables, by_param, -1.0)
+
+    def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):
+        if full_cov or full_output_cov:
+            raise NotImplementedError("predict_f(full_cov=True) is not on the reference path")
+        eng = self._get_engine()
+        Z, qmu, Lq = self._device_params()
+        M, D = Z.shape
+        Xs = ops.to_device(Xnew, self._device_index, ndim=2)
+        if Xs.shape[1] != D:
+            raise ValueError(f"Xnew has {Xs.shape[1]} columns, Z has {D}")
+        ck = self._lower_kernel(D)
+        Ns = Xs.shape[0]
+        out = torch.empty((2, Ns), dtype=torch.float64, device=Xs.device)
+        eng.svgp_predict_f(ck.theta(), Z.data_ptr(), M, D, qmu.data_ptr(), Lq.data_ptr(), M, Xs.data_ptr(), Ns,
+                           out[0].data_ptr(), out[1].data_ptr())
+        return _out(out[0][:, None]), _out(out[1][:, None])
