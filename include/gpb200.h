@@ -197,6 +197,12 @@ int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, 
                        const double* d_qmu, const double* d_qsqrt, int64_t ldq, const double* d_Xs,
                        int64_t Ns, double* d_mean, double* d_var);
 
+/* Adam update of a device-resident parameter block in place (x += / -= lr * mhat / (sqrt(vhat) + eps));
+ * used by the data-parallel minibatch SVGP loop for Z, q_mu, q_sqrt (identity transforms), where
+ * GPflow users run tf.optimizers.Adam on minibatches.  step >= 1 is the 1-based iteration. */
+int gpb_adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double* d_v, int64_t n,
+                  double lr, double beta1, double beta2, double eps, int64_t step, int maximize);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,7 @@ SIGNATURES = {
     "gpb_svgp_data_term": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _P, _I64, _P, _INT]),
     "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
     "gpb_svgp_predict_f": (_INT, [_P, _DP, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
+    "gpb_adam_step": (_INT, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _I64, _INT]),
 }
 
 
@@ -259,3 +260,8 @@ class Engine:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         self._check(self._lib.gpb_svgp_predict_f(self._h, _as_dp(theta), _P(dZ), M, D, _P(dqmu), _P(dqsqrt), ldq, _P(dXs),
                                                  Ns, _P(dmean), _P(dvar)), "gpb_svgp_predict_f")
+
+    def adam_step(self, dx: int, dg: int, dm: int, dv: int, n: int, lr: float, step: int, beta1=0.9, beta2=0.999,
+                  eps=1e-8, maximize: bool = True):
+        self._check(self._lib.gpb_adam_step(self._h, _P(dx), _P(dg), _P(dm), _P(dv), n, float(lr), float(beta1),
+                                            float(beta2), float(eps), int(step), int(bool(maximize))), "gpb_adam_step")

@@ -613,3 +613,41 @@ int svgp_predict_f(gpb_handle* h, const double* theta, const double* d_Z, int64_
 }
 
 }  // namespace gpb
+
+namespace gpb {
+
+// Adam on a device-resident parameter block (the SVGP variational parameters and inducing points
+// have identity transforms, so they are updated in place on the device; the handful of
+// constrained hyper-parameters are stepped by the host layer).  sign = +1 ascends (ELBO).
+__global__ void adam_step_kernel(double* __restrict__ x, const double* __restrict__ g, double* __restrict__ m,
+                                 double* __restrict__ v, int64_t n, double lr, double b1, double b2, double eps,
+                                 double c1, double c2, double sign) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double gi = g[i];
+    const double mi = b1 * m[i] + (1.0 - b1) * gi;
+    const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    x[i] += sign * lr * (mi / c1) / (sqrt(vi / c2) + eps);
+}
+
+int adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double* d_v, int64_t n, double lr, double b1,
+              double b2, double eps, int64_t step, double sign) {
+    if (n <= 0) return 0;
+    const double c1 = 1.0 - pow(b1, (double)step), c2 = 1.0 - pow(b2, (double)step);
+    adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_x, d_g, d_m, d_v, n, lr, b1, b2, eps, c1, c2, sign);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "adam_step_kernel launch");
+}
+
+}  // namespace gpb
+
+extern "C" int gpb_adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double* d_v, int64_t n, double lr,
+                             double beta1, double beta2, double eps, int64_t step, int maximize) {
+    if (!h) return -1;
+    cudaError_t e_ = cudaSetDevice(h->device);
+    if (e_ != cudaSuccess) return gpb::check_cuda(h, e_, "cudaSetDevice");
+    if (!d_x || !d_g || !d_m || !d_v || step < 1) return gpb::set_error(h, -2, "adam_step: bad arguments");
+    return gpb::adam_step(h, d_x, d_g, d_m, d_v, n, lr, beta1, beta2, eps, step, maximize ? 1.0 : -1.0);
+}

@@ -11,6 +11,13 @@ from tests.helpers import make_multi_input, to_oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _direct_form():
+    O.set_distance_form("direct")   # the numpy oracle evaluates distances as the CUDA kernels do
+    yield
+    O.set_distance_form("gram")
+
+
 def _kernels(gp, D):
     K = gp.kernels
     last = [D - 1]
@@ -106,3 +113,21 @@ def test_reference_call_pattern_svgp(gp):
     mean, var = model.predict_f(X)
     assert float(np.mean((mean.numpy() - Y) ** 2)) < 0.05
     assert model.inducing_variable.Z.numpy().shape == (20, 1)
+
+
+def test_data_parallel_trainer_single_rank(gp):
+    """SVGPDataParallel on one rank: the ELBO it reports equals SVGP.elbo at the same parameters, and
+    Adam steps increase it."""
+    from portfoliooptgp_b200.svgp_dp import SVGPDataParallel
+    X, Y = make_multi_input(91, 4096, 4)
+    Z = X[:64].copy()
+    k = gp.kernels.SquaredExponential(lengthscales=1.5)
+    tr = SVGPDataParallel(k, 1e-1, Z, num_data=4096, X_shard=X, Y_shard=Y, minibatch_size=1024, lr=5e-2)
+    e0 = tr.step(update=False)
+    m = gp.models.SVGP(gp.kernels.SquaredExponential(lengthscales=1.5), gp.likelihoods.Gaussian(1e-1), Z, num_data=4096)
+    assert e0 == pytest.approx(float(m.elbo((X[:1024], Y[:1024]))), rel=1e-12)
+    tr.cursor = 0
+    first = tr.step()
+    vals = [tr.step() for _ in range(40)]
+    assert np.mean(vals[-4:]) > first + 100.0
+    assert np.allclose(np.triu(tr.q_sqrt.cpu().numpy(), 1), 0.0)

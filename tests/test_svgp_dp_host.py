@@ -1,0 +1,57 @@
+"""CPU, gloo world_size 2: the data-parallel SVGP reduction (sum the unscaled data-term records,
+scale once by num_data/(world*B), subtract the KL once) reproduces the single-process ELBO."""
+import os
+import socket
+
+import numpy as np
+
+from oracle import gpflow_oracle as O
+
+
+def _problem():
+    rng = np.random.default_rng(0)
+    N, M = 64, 9
+    X = rng.standard_normal((N, 2)); Y = rng.standard_normal((N, 1))
+    Z = X[:M] + 0.05
+    qmu = 0.2 * rng.standard_normal((M, 1))
+    qs = (0.7 * np.eye(M) + 0.05 * np.tril(rng.standard_normal((M, M))))[None]
+    k = O.Sum([O.Leaf("se", 1.1, 0.9), O.Leaf("linear", 0.2)])
+    return k, X, Y, Z, qmu, qs
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from portfoliooptgp_b200.svgp_dp import allreduce_sum_, combine_records
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    k, X, Y, Z, qmu, qs = _problem()
+    B = X.shape[0] // world
+    Xr, Yr = X[rank * B:(rank + 1) * B], Y[rank * B:(rank + 1) * B]
+    kl = O.gauss_kl(qmu, qs)
+    S_local = O.svgp_elbo(k, Z, qmu, qs, 0.1, Xr, Yr, num_data=None) + kl      # unscaled data term of this rank
+    flat = torch.tensor([S_local, float(rank + 1)], dtype=torch.float64)
+    allreduce_sum_(flat)
+    elbo = combine_records(float(flat[0]), kl, num_data=200, world=world, B=B)
+    q.put((rank, elbo, float(flat[1])))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_elbo_reduction_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    k, X, Y, Z, qmu, qs = _problem()
+    want = O.svgp_elbo(k, Z, qmu, qs, 0.1, X, Y, num_data=200)   # one process, the union of both minibatches
+    for _, elbo, tag in outs:
+        assert abs(elbo - want) <= 1e-12 * abs(want)
+        assert tag == 3.0
