@@ -275,6 +275,17 @@ def run_gpu(args):
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "ms": asm_ms, "algorithmic_bytes": asm_bytes, "peak_source": peaks["hbm_source"]}
 
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras["c3_batched"] = bench_c3(gpflow, torch, dist, world, rank, barrier)
+        except Exception as e:  # an extra must never take the headline line down
+            extras["c3_batched"] = {"error": repr(e)}
+        try:
+            extras["c5_svgp"] = bench_c5(gpflow, torch, dist, world, rank, barrier, eng)
+        except Exception as e:
+            extras["c5_svgp"] = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,9 +306,102 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "assembly_roofline": assembly,
             "kernel_ms_per_step": breakdown, "cpu_baseline": cpu, "lml": lml}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(torch, dist, world, ms):
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
+    """BASELINE config C3: 20 stocks x 64 rolling windows x 4 restarts = 5120 independent GPs of N=128,
+    D=8 (reference kernel Exponential[0:7] * Exponential[7], Multi-Input_GPR/main.py:126-135,525),
+    contiguous block partition over the ranks, no data-path collective, one final gather."""
+    from portfoliooptgp_b200.batched import gather_results, shard_range
+    assets, windows, restarts, N, D = 20, 64, 4, 128, 8
+    total = assets * windows * restarts
+    lo, hi = shard_range(total, rank, world)
+    rng = np.random.default_rng(3)
+    series = [make_c2(seed=100 + a, n=N + windows - 1, d=D) for a in range(assets)]
+    starts = np.array([1e-5, 1e-3, 1e-1, 1.0])
+    Xb = np.empty((hi - lo, N, D)); Yb = np.empty((hi - lo, N)); nz = np.empty(hi - lo)
+    for g in range(lo, hi):
+        a, rem = divmod(g, windows * restarts)
+        w, r = divmod(rem, restarts)
+        Xb[g - lo] = series[a][0][w:w + N]
+        Yb[g - lo] = series[a][1][w:w + N, 0]
+        nz[g - lo] = max(starts[r], 2e-6)
+    K = gpflow.kernels
+    k = K.Exponential(active_dims=slice(0, D - 1)) * K.Exponential(active_dims=slice(D - 1, D))
+    m = gpflow.BatchedGPR(Xb, Yb, k, noise_variance=nz, train_noise=True)
+    th = torch.from_numpy(m.theta).cuda(); nzd = torch.from_numpy(m.noise).cuda()
+    eng = m._engine
+
+    def one():
+        eng.batched_lml_grad(m.X.data_ptr(), m.Y.data_ptr(), th.data_ptr(), nzd.data_ptr(), m.B, m.N, m.D,
+                             m._out.data_ptr(), m._info.data_ptr(), True)
+
+    eng.set_kernel(m.compiled.spec, m.compiled.token)
+    for _ in range(3):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one()
+    e1.record()
+    barrier()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / iters
+    full = gather_results(m._out[:, :1].contiguous(), total)   # the single collective of this path
+    ok = bool(torch.isfinite(full).all().item())
+    # algorithmic work per GP per eval (SURVEY.md 8d): N^3 + ~60 N^2 flop
+    flops = total * (N ** 3 + 60.0 * N ** 2)
+    return {"workload": "C3: 5120 GPs (20x64x4), N=128, D=8, Exponential*Exponential, LML+grad, one GP per CTA",
+            "gp_evals_per_s": total / (ms * 1e-3), "ms_per_batched_eval": ms, "gps_total": total, "gps_per_rank": hi - lo,
+            "n_gpus": world, "gflops_algorithmic": flops / (ms * 1e-3) / 1e9, "gathered_finite": ok}
+
+
+def bench_c5(gpflow, torch, dist, world, rank, barrier, eng, steps=3):
+    """BASELINE config C5: SVGP M=2048 inducing points, minibatch B=65536 per GPU, D=8, N=16M rows,
+    data-parallel with one all-reduce of the flat gradient record per step."""
+    from portfoliooptgp_b200.svgp_dp import SVGPDataParallel
+    M, B, D, N = 2048, 65536, 8, 16 * 2 ** 20
+    shard_rows = min(N // world, 4 * B)   # resident window of this rank's shard (synthetic rows)
+    g = torch.Generator(device="cuda"); g.manual_seed(5 + rank)
+    X = torch.randn((shard_rows, D), dtype=torch.float64, device="cuda", generator=g)
+    w = torch.randn((D, 1), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    Y = torch.sin(X @ w) + 0.1 * torch.randn((shard_rows, 1), dtype=torch.float64, device="cuda", generator=g)
+    Z = torch.randn((M, D), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    tr = SVGPDataParallel(gpflow.kernels.SquaredExponential(lengthscales=2.0), 1e-2, Z, num_data=N, X_shard=X, Y_shard=Y,
+                          minibatch_size=B, lr=1e-3)
+    tr.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        elbo = tr.step()
+    e1.record()
+    barrier()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
+    eng.profile_enable(True)
+    tr.step()
+    ms_cat, n_cat = eng.profile_read()
+    eng.profile_enable(False)
+    flops = 6.0 * M * M * B
+    peaks = measured_peaks()
+    return {"workload": "C5: SVGP M=2048, minibatch 65536/GPU, D=8, SquaredExponential, ELBO+grad+Adam step, data-parallel",
+            "steps_per_s": 1e3 / ms, "ms_per_step": ms, "rows_per_s": world * B / (ms * 1e-3), "n_gpus": world,
+            "allreduce_doubles": int(tr.flat.numel()), "elbo": elbo,
+            "gemm_ms": ms_cat["gemm"], "gemm_tflops_algorithmic": flops / (ms_cat["gemm"] * 1e-3) / 1e12,
+            "gemm_frac_of_fp64_peak": flops / (ms_cat["gemm"] * 1e-3) / 1e12 / peaks["fp64_tflops"],
+            "kernel_ms": {c: ms_cat[c] for c in ms_cat if n_cat[c]}}
 
 
 def main():
@@ -307,6 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 (batched) and C5 (SVGP) side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
