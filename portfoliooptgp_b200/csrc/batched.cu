@@ -35,7 +35,7 @@ constexpr size_t batched_smem_bytes() { return (size_t)(BatchedSmem::XS + 128 * 
 
 // mode 0: LML only; 1: LML + gradient; 2: predict_f at Ns points per GP
 template <int DP>
-__global__ void __launch_bounds__(BT)
+__global__ void __launch_bounds__(BT, 1)
 batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __restrict__ X,
                   const double* __restrict__ Yc, const double* __restrict__ theta, const double* __restrict__ noise,
                   int N, int D, int mode, double* __restrict__ out, int* __restrict__ info,
