@@ -36,17 +36,26 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     int* fail = reinterpret_cast<int*>(dinv + DINV_DOUBLES);
     const int tid = threadIdx.x;
     const int np = (n + 7) & ~7;
-    for (int idx = tid; idx < np * NB; idx += LEAF_THREADS) {
-        const int i = idx >> 7, j = idx & (NB - 1);
-        if (j >= np) continue;
-        double v = 0.0;
-        if (i < n && j <= i) v = A[(int64_t)i * lda + j];
-        else if (i >= n && i == j) v = 1.0;
-        S[i * SLD + j] = v;
+    // 128 x 128 block, 512 threads: 32 elements per thread, all loads in flight before the stores
+    {
+        double v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const int idx = tid + u * LEAF_THREADS;
+            const int i = idx >> 7, j = idx & (NB - 1);
+            v[u] = (i < n && j <= i) ? A[(int64_t)i * lda + j] : ((i >= n && i == j) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const int idx = tid + u * LEAF_THREADS;
+            const int i = idx >> 7, j = idx & (NB - 1);
+            if (i < np && j < np) S[i * SLD + j] = v[u];
+        }
     }
     __syncthreads();
     block_potrf_lower(S, np, fail, dinv);
     if (tid == 0 && *fail != 0) atomicCAS(info, 0, offset + *fail);
+#pragma unroll 8
     for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
         if (j < n) A[(int64_t)i * lda + j] = S[i * SLD + j];
@@ -61,6 +70,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     }
     __syncthreads();
     block_trtri_lower_inplace(S, np, T, dinv);
+#pragma unroll 8
     for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
         if (j < n) W[(int64_t)i * ldw + j] = S[i * SLD + j];

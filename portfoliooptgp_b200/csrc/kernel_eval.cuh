@@ -373,6 +373,13 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
     double total = 0.0;
     for (int t = 0; t < kp.n_terms; ++t) {
         const DevTerm& tm = kp.terms[t];
+        if (tm.n_factors == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
+            const int id = tm.leaf[0];
+            total += sel4(v, id);
+#pragma unroll
+            for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? wgt : 0.0;
+            continue;
+        }
         double fv[GPB_MAX_FACTORS];
         double prod = 1.0;
 #pragma unroll
@@ -472,6 +479,13 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
     double total = 0.0;
     for (int t = 0; t < kp.n_terms; ++t) {
         const DevTerm& tm = kp.terms[t];
+        if (tm.n_factors == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
+            const int id = tm.leaf[0];
+            total += sel4(v, id);
+#pragma unroll
+            for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? wgt : 0.0;
+            continue;
+        }
         double fv[GPB_MAX_FACTORS];
         double prod = 1.0;
 #pragma unroll
