@@ -65,88 +65,106 @@ __device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const doub
 // inverses of the diagonal blocks (block b at dinv + b*8*DLD, row-major, stride DLD, zero upper).
 // *fail (shared int) = 1-based index of the first non-positive pivot, 0 if none; a failing pivot is
 // replaced by 1 so that no NaNs propagate.
+// (a) one warp, every lane redundantly: factor the 8x8 diagonal block at (p, p) in registers, invert the
+// factor, store L_pp (zero strict upper) and M = L_pp^-1.
+__device__ __forceinline__ void warp_diag_factor(double* S, int p, int* fail, double* M) {
+    const int lane = threadIdx.x & 31;
+    double a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = S[(p + r) * SLD + p + c];
+    double rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double d = a[j][j];
+        if (!(d > 0.0)) {
+            if (lane == 0 && *fail == 0) *fail = p + j + 1;
+            d = 1.0;
+        }
+        rs[j] = rsqrt(d);
+        a[j][j] = d * rs[j];
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r) a[r][j] *= rs[j];
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r)
+#pragma unroll
+            for (int k = j + 1; k <= r; ++k) a[r][k] = fma(-a[r][j], a[k][j], a[r][k]);
+    }
+    // inverse of the factor: lane c (mod 8) solves column c; 1/L_jj = rs[j]
+    double x[8];
+    const int c = lane & 7;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) v = fma(-a[r][k], x[k], v);
+        x[r] = (r >= c) ? v * rs[r] : 0.0;
+    }
+    // write back: lane r (< 8) writes row r of L (static register indices via the unrolled select)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (lane == r) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) S[(p + r) * SLD + p + cc] = (cc <= r) ? a[r][cc] : 0.0;
+        }
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) M[r * DLD + c] = x[r];
+    }
+}
+
+__device__ __forceinline__ void warp_trailing_tile(double* S, int p, int t) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    int ti, tj;
+    tri_tile(t, ti, tj);
+    double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
+    double2 cc = *reinterpret_cast<double2*>(C);
+    const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
+    const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
+    warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
+    *reinterpret_cast<double2*>(C) = cc;
+}
+
 __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* dinv) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
     if (tid == 0) *fail = 0;
     __syncthreads();
-    for (int p = 0; p < np; p += 8) {
-        double* M = dinv + (p >> 3) * 8 * DLD;
-        if (warp == 0) {
-            // (a) all 32 lanes hold the whole lower triangle (broadcast loads) and run the same code
-            double a[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) a[r][c] = S[(p + r) * SLD + p + c];
-            double rs[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double d = a[j][j];
-                if (!(d > 0.0)) {
-                    if (lane == 0 && *fail == 0) *fail = p + j + 1;
-                    d = 1.0;
-                }
-                rs[j] = rsqrt(d);
-                a[j][j] = d * rs[j];
-#pragma unroll
-                for (int r = j + 1; r < 8; ++r) a[r][j] *= rs[j];
-#pragma unroll
-                for (int r = j + 1; r < 8; ++r)
-#pragma unroll
-                    for (int k = j + 1; k <= r; ++k) a[r][k] = fma(-a[r][j], a[k][j], a[r][k]);
-            }
-            // inverse of the factor: lane c (mod 8) solves column c; 1/L_jj = rs[j]
-            double x[8];
-            const int c = lane & 7;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                double v = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < r; ++k) v = fma(-a[r][k], x[k], v);
-                x[r] = (r >= c) ? v * rs[r] : 0.0;
-            }
-            // write back: lane r (< 8) writes row r of L (static register indices via the unrolled select)
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (lane == r) {
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) S[(p + r) * SLD + p + cc] = (cc <= r) ? a[r][cc] : 0.0;
-                }
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) M[r * DLD + c] = x[r];
-            }
+    if (warp == 0) warp_diag_factor(S, 0, fail, dinv);
+    __syncthreads();
+    for (int p = 0; p + 8 < np; p += 8) {
+        const double* M = dinv + (p >> 3) * 8 * DLD;
+        const int mt = (np - p - 8) >> 3;
+        // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
+        for (int ti = warp; ti < mt; ti += nwarps) {
+            double* Pt = S + (p + 8 + ti * 8) * SLD + p;
+            double c0 = 0.0, c1 = 0.0;
+            warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+            __syncwarp();
+            *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
         }
         __syncthreads();
-        const int m = np - p - 8;  // rows below the block
-        if (m > 0) {
-            const int mt = m >> 3;
-            // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
-            for (int ti = warp; ti < mt; ti += nwarps) {
-                double* Pt = S + (p + 8 + ti * 8) * SLD + p;
-                double c0 = 0.0, c1 = 0.0;
-                warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+        // (c) trailing update C -= P_ti P_tj^T over the 8x8 tiles (ti >= tj) of the trailing matrix, with
+        // look-ahead: warp 0 updates the next diagonal block (tile 0) and factors it at once, while the
+        // other warps apply the rest of the update.
+        const int ntiles = mt * (mt + 1) / 2;
+        if (nwarps > 1) {
+            if (warp == 0) {
+                warp_trailing_tile(S, p, 0);
                 __syncwarp();
-                *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
+                warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
+            } else {
+                for (int t = warp; t < ntiles; t += nwarps - 1) warp_trailing_tile(S, p, t);
             }
-            __syncthreads();
-            // (c) trailing update, 8x8 tiles (ti >= tj) of the trailing matrix: C -= P_ti P_tj^T
-            const int ntiles = mt * (mt + 1) / 2;
-            for (int t = warp; t < ntiles; t += nwarps) {
-                int ti, tj;
-                tri_tile(t, ti, tj);
-                double* C = S + (p + 8 + ti * 8 + g) * SLD + p + 8 + tj * 8 + 2 * q;
-                double2 cc = *reinterpret_cast<double2*>(C);
-                const double* Pi = S + (p + 8 + ti * 8) * SLD + p;
-                const double* Pj = S + (p + 8 + tj * 8) * SLD + p;
-                warp_tile_mma(cc.x, cc.y, Pi, SLD, 1, Pj, 1, SLD, 8, -1.0);
-                *reinterpret_cast<double2*>(C) = cc;
-            }
-            __syncthreads();
+        } else {
+            for (int t = 0; t < ntiles; ++t) warp_trailing_tile(S, p, t);
+            __syncwarp();
+            warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
         }
+        __syncthreads();
     }
 }
 
