@@ -276,9 +276,10 @@ static int launch_layout(gpb_handle* h, const GemmParams& p, cudaStream_t stream
     const int64_t mid_tiles = p.tri ? ((int64_t)((p.M + 63) / 64) * ((p.M + 63) / 64 + 1) / 2)
                                     : ((int64_t)((p.M + 63) / 64) * ((p.N + 63) / 64));
     if (mid_tiles >= h->sm_count)
-        return launch_cfg<64, 64, 16, 32, 32, 3, AKC, BKC>(h, p, stream);
+        return launch_cfg<64, 64, 32, 32, 32, 2, AKC, BKC>(h, p, stream);
     // latency-bound regime (the bottom of the Cholesky recursion): spread over as many SMs as possible
-    return launch_cfg<32, 32, 16, 16, 16, 3, AKC, BKC>(h, p, stream);
+    // and keep the number of dependent load round trips small (BK = 64: K = 128 is two k-tiles)
+    return launch_cfg<32, 32, 64, 16, 16, 2, AKC, BKC>(h, p, stream);
 }
 
 int launch_gemm(gpb_handle* h, const GemmArgs& a, cudaStream_t stream) {

@@ -1,0 +1,95 @@
+"""Golden fixtures (tests/golden/reference_call_pattern.npz, made by tests/golden/make_golden.py from
+the reference's real AAPL CSVs with its own preprocessing and kernel candidates).
+
+CPU part: the oracle reproduces the committed fixtures (drift guard).
+GPU part: the CUDA path, through the GPflow-shaped API, matches the fixtures.  For the
+reference-faithful sigma^2 = 1e-5 the covariance is ill-conditioned (cond up to ~1e8 on the raw
+day-index axis), so the bar is the condition-scaled bound c * cond(K) * eps, c = 50;
+for sigma^2 = 1e-2 it is the north-star bar (1e-9 values, 1e-7 gradients)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gpflow_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_call_pattern.npz"))
+EPS = np.finfo(np.float64).eps
+
+
+def _oracle_kernels():
+    L = O.Leaf
+    return {
+        "SE": L("se"), "Matern12": L("matern12"), "RQ": L("rq"), "Exponential": L("exponential"),
+        "SE+Matern12": O.Sum([L("se"), L("matern12")]),
+        "Exp+Periodic(SE)+Linear": O.Sum([L("exponential"), O.Periodic(L("se"), 1.0), L("linear")]),
+        "Exp+Periodic(SE)": O.Sum([L("exponential"), O.Periodic(L("se"), 1.0)]),
+        "SE*Matern12": O.Product([L("se"), L("matern12")]),
+    }
+
+
+def _gp_kernels(gpflow):
+    K = gpflow.kernels   # GPR/main.py:105-114
+    return {
+        "SE": K.SquaredExponential(), "Matern12": K.Matern12(), "RQ": K.RationalQuadratic(), "Exponential": K.Exponential(),
+        "SE+Matern12": K.SquaredExponential() + K.Matern12(),
+        "Exp+Periodic(SE)+Linear": K.Exponential() + K.Periodic(K.SquaredExponential()) + K.Linear(),
+        "Exp+Periodic(SE)": K.Exponential() + K.Periodic(K.SquaredExponential()),
+        "SE*Matern12": K.SquaredExponential() * K.Matern12(),
+    }
+
+
+def test_oracle_reproduces_golden():
+    assert list(G["kernel_names"]) == list(_oracle_kernels())
+    for period in ("d", "w", "m"):
+        X, Y = G[f"aapl_{period}_X"], G[f"aapl_{period}_Y"]
+        assert X.shape[0] == {"d": 89, "w": 19, "m": 5}[period]
+        for name, k in _oracle_kernels().items():
+            key = f"aapl_{period}|{name}|1e-2"
+            lml, g, gn = O.gpr_lml_and_grad(k, X, Y, 1e-2)
+            assert lml == pytest.approx(float(G[key + "|lml"]), rel=1e-12)
+            assert np.allclose(np.concatenate([g, [gn]]), G[key + "|grad"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("period", ["d", "w", "m"])
+@pytest.mark.parametrize("tag,s2", [("1e-2", 1e-2), ("1e-5", 1e-5)])
+def test_gpu_matches_golden_gpr(gp, period, tag, s2):
+    X, Y, Xs = G[f"aapl_{period}_X"], G[f"aapl_{period}_Y"], G[f"aapl_{period}_Xs"]
+    for name, k in _gp_kernels(gp).items():
+        key = f"aapl_{period}|{name}|{tag}"
+        cond = float(G[key + "|cond"])
+        tol_v = max(1e-9, 50 * cond * EPS)
+        tol_g = max(1e-7, 50 * cond * EPS)
+        model = gp.models.GPR(data=(X, Y), kernel=k)                 # GPR/model_trainer.py:15-17
+        model.likelihood.variance.assign(s2)
+        gp.set_trainable(model.likelihood.variance, False)
+        lml, g, gn = model.lml_and_constrained_grads()
+        l0, g0 = float(G[key + "|lml"]), G[key + "|grad"]
+        assert abs(lml - l0) <= tol_v * max(1.0, abs(l0)), (key, lml, l0, cond)
+        assert np.max(np.abs(np.concatenate([g, [gn]]) - g0)) <= tol_g * max(1.0, np.max(np.abs(g0))), (key, cond)
+        mean, var = model.predict_f(Xs, full_cov=False)              # GPR/predictor.py:6
+        m0, v0 = G[key + "|mean"], G[key + "|var"]
+        assert np.max(np.abs(mean.numpy() - m0)) <= tol_v * max(1.0, np.max(np.abs(m0))), (key, cond)
+        assert np.max(np.abs(var.numpy() - v0)) <= tol_v * max(1.0, np.max(np.abs(v0))), (key, cond)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_multi_input_and_svgp(gp):
+    Xm, Ym = G["multi_X"], G["multi_Y"]
+    N, D = 67, 7
+    K = gp.kernels
+    k = K.Exponential(active_dims=slice(0, D - 1)) * K.Exponential(active_dims=slice(D - 1, D))
+    m = gp.models.GPR((Xm[:N], Ym[:N]), kernel=k, noise_variance=1e-3)     # Multi-Input_GPR/main.py:421-423
+    lml, g, gn = m.lml_and_constrained_grads()
+    assert abs(lml - float(G["multi|lml"])) <= 1e-9 * abs(float(G["multi|lml"]))
+    assert np.max(np.abs(np.concatenate([g, [gn]]) - G["multi|grad"])) <= 1e-7 * max(1.0, np.max(np.abs(G["multi|grad"])))
+    mean, var = m.predict_f(Xm, full_cov=False)                             # main.py:434, last row is the forecast
+    assert np.max(np.abs(mean.numpy() - G["multi|mean"])) <= 1e-9 * max(1.0, np.max(np.abs(G["multi|mean"])))
+    assert np.max(np.abs(var.numpy() - G["multi|var"])) <= 1e-9
+    X, Y = G["aapl_d_X"], G["aapl_d_Y"]
+    sv = gp.models.SVGP(kernel=K.SquaredExponential(lengthscales=10.0), likelihood=gp.likelihoods.Gaussian(variance=1e-2),
+                        inducing_variable=G["svgp_Z"], num_data=len(X), q_mu=G["svgp_qmu"], q_sqrt=G["svgp_qsqrt"])
+    assert float(sv.elbo((X, Y))) == pytest.approx(float(G["svgp|elbo"]), rel=1e-9)
+    mean, var = sv.predict_f(X)
+    assert np.max(np.abs(mean.numpy() - G["svgp|mean"])) <= 1e-9 and np.max(np.abs(var.numpy() - G["svgp|var"])) <= 1e-9
