@@ -254,12 +254,34 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel (DMMA GEMM), timed live with CUDA events per launch
     peaks = measured_peaks()
+    eng.set_option(eng.OPTION_FORK_STREAMS, 0)   # serialise the launches so that event pairs time one kernel each
     eng.profile_enable(True)
     prof_steps = max(1, min(args.steps, 3))
     for _ in range(prof_steps):
         step()
     ms_cat, n_cat = eng.profile_read()
     eng.profile_enable(False)
+    eng.set_option(eng.OPTION_FORK_STREAMS, 1)
+    # the Cholesky trailing update on its own (north_star target): A22 -= T T^T at the top of the recursion
+    n2 = N_C2 // 2
+    Tm = torch.randn((n2, n2), dtype=torch.float64, device="cuda")
+    A22 = torch.zeros((n2, n2), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        eng.gemm(0, 1, n2, n2, n2, -1.0, Tm.data_ptr(), n2, Tm.data_ptr(), n2, 1.0, A22.data_ptr(), n2, 1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        eng.gemm(0, 1, n2, n2, n2, -1.0, Tm.data_ptr(), n2, Tm.data_ptr(), n2, 1.0, A22.data_ptr(), n2, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    syrk_ms = e0.elapsed_time(e1) / 5
+    syrk_tf = float(n2) ** 3 / (syrk_ms * 1e-3) / 1e12     # n2^2 * K flop (lower triangle of a rank-K update)
+    del Tm, A22
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_dgemm_summary.json")))["per_step"]["traffic_bytes"]
+    except Exception:
+        pass
     gemm_ms_step = ms_cat["gemm"] / prof_steps
     flops_step = float(N_C2) ** 3  # N^3/3 factor + N^3/3 inverse + N^3/3 K^-1
     achieved_tf = flops_step / (gemm_ms_step * 1e-3) / 1e12
@@ -267,7 +289,10 @@ def run_gpu(args):
     asm_bytes = 8.0 * N_C2 * (N_C2 + 1) / 2 + 8.0 * D_C2 * N_C2 * 2
     roofline = {"bound": "tensor", "kernel": "dgemm_kernel (DMMA.8x8x4): Cholesky trailing update + panel/inverse/K^-1 products",
                 "achieved": achieved_tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["fp64_tflops"],
-                "traffic": None, "peak_source": peaks["fp64_source"],
+                "traffic": traffic, "traffic_note": "DRAM bytes of the 13 big launches of one step, ncu --set full (profiles/r01_ncu_full_dgemm_summary.json)",
+                "peak_source": peaks["fp64_source"],
+                "trailing_update": {"shape": "SYRK n=4096, K=4096, lower tiles", "ms": syrk_ms, "achieved": syrk_tf,
+                                    "frac": syrk_tf / peaks["fp64_tflops"], "unit": "TFLOP/s"},
                 "launches_per_step": n_cat["gemm"] / prof_steps, "ms_per_step": gemm_ms_step,
                 "algorithmic_flops_per_step": flops_step}
     breakdown = {c: ms_cat[c] / prof_steps for c in ms_cat if n_cat[c]}

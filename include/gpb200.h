@@ -99,6 +99,10 @@ int gpb_version(void);
 /* Number of engine kernels launched through this handle since creation (bench.py gpu_launches). */
 int64_t gpb_launch_count(gpb_handle* h);
 
+/* Engine options.  option 0: fork off-critical-path products of the blocked factorisation onto side
+ * streams (default 1; bench.py switches it off while it times individual kernels). */
+int gpb_set_option(gpb_handle* h, int option, int value);
+
 /* Optional kernel timing with CUDA events recorded on the handle's stream around each engine
  * launch, by category (0 DMMA GEMM, 1 assembly, 2 Cholesky leaf, 3 fused gradient reduction,
  * 4 vector kernels, 5 batched, 6 SVGP).  gpb_profile_read synchronises, returns the summed

@@ -71,6 +71,7 @@ SIGNATURES = {
     "gpb_last_error": (C.c_char_p, [_P]),
     "gpb_set_stream": (_INT, [_P, _P]),
     "gpb_launch_count": (_I64, [_P]),
+    "gpb_set_option": (_INT, [_P, _INT, _INT]),
     "gpb_profile_enable": (_INT, [_P, _INT]),
     "gpb_profile_read": (_INT, [_P, _DP, C.POINTER(C.c_int64)]),
     "gpb_set_kernel": (_INT, [_P, C.POINTER(GpbKernelSpec)]),
@@ -160,6 +161,11 @@ class Engine:
         return int(self._lib.gpb_launch_count(self._h))
 
     PROF_CATEGORIES = ("gemm", "assemble", "leaf", "grad_reduce", "vector", "batched", "svgp", "other")
+
+    OPTION_FORK_STREAMS = 0
+
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.gpb_set_option(self._h, int(option), int(value)), "gpb_set_option")
 
     def profile_enable(self, on: bool):
         self._check(self._lib.gpb_profile_enable(self._h, int(bool(on))), "gpb_profile_enable")

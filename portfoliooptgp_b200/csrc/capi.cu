@@ -212,6 +212,14 @@ int gpb_set_stream(gpb_handle* h, void* cuda_stream) {
 
 int64_t gpb_launch_count(gpb_handle* h) { return h ? h->launches : -1; }
 
+int gpb_set_option(gpb_handle* h, int option, int value) {
+    if (!h) return -1;
+    switch (option) {
+        case 0: h->fork_streams = (value != 0); return 0;
+        default: return set_error(h, -2, "unknown option %d", option);
+    }
+}
+
 int gpb_profile_enable(gpb_handle* h, int on) {
     if (!h) return -1;
     h->profile = (on != 0);

@@ -113,7 +113,7 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
     g.A = A21; g.lda = lda; g.B = W11; g.ldb = ldw; g.C = W21; g.ldc = ldw; g.b_upper = 1;
     if ((rc = launch_gemm(h, g, h->stream))) return rc;
     // fork point: everything that only needs T (and W11) may start now
-    const bool fork = (depth < gpb_handle::MAX_DEPTH) && h->side[depth] && n2 >= 2 * NB;
+    const bool fork = h->fork_streams && (depth < gpb_handle::MAX_DEPTH) && h->side[depth] && n2 >= 2 * NB;
     cudaStream_t us = fork ? h->side[depth] : h->stream;
     if (fork) {
         cudaError_t e = cudaEventRecord(h->ev_fork[depth], h->stream);

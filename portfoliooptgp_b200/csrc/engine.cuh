@@ -18,6 +18,7 @@ struct gpb_handle {
     cudaStream_t side[MAX_DEPTH] = {};
     cudaEvent_t ev_fork[MAX_DEPTH] = {}, ev_join[MAX_DEPTH] = {};
     std::string err;
+    bool fork_streams = true;   // gpb_set_option(h, 0, x)
     int64_t launches = 0;
     int sm_count = 148;
 
