@@ -77,7 +77,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -201,12 +201,12 @@ def run_gpu(args):
     def step():
         return model.lml_and_constrained_grads()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # started before the warm-up so that several samples fall under load
     for _ in range(args.warmup):
         step()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -301,6 +301,11 @@ def run_gpu(args):
                 "ms": asm_ms, "algorithmic_bytes": asm_bytes, "peak_source": peaks["hbm_source"]}
 
     extras = {}
+    if not args.no_extras and rank == 0:
+        try:
+            extras["c1_fit"] = bench_c1(gpflow, torch)
+        except Exception as e:
+            extras["c1_fit"] = {"error": repr(e)}
     if not args.no_extras:
         try:
             extras["c3_batched"] = bench_c3(gpflow, torch, dist, world, rank, barrier)
@@ -343,6 +348,38 @@ def _max_over_ranks(torch, dist, world, ms):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     return ms
+
+
+def bench_c1(gpflow, torch):
+    """BASELINE config C1: single-input GPR, N = 1000 daily points, kernel SE + Periodic(SE), noise frozen,
+    Scipy L-BFGS-B maxiter=100 + predict_f -- the call pattern of GPR/model_trainer.py:15-20 (latency-bound)."""
+    rng = np.random.default_rng(1)
+    n = 1000
+    t = np.arange(n, dtype=np.float64)[:, None]
+    X = (t - t.mean()) / t.std()
+    r = rng.normal(0, 0.01, size=(n, 1)) + 0.004 * np.sin(2 * np.pi * t / 21.0)
+    Y = (r - r.mean()) / r.std()
+    K = gpflow.kernels
+    out = {}
+    for tag, s2 in (("noise_1e-2", 1e-2), ("noise_1e-5_reference", 1e-5)):
+        k = K.SquaredExponential() + K.Periodic(K.SquaredExponential())
+        m = gpflow.models.GPR(data=(X, Y), kernel=k)
+        m.likelihood.variance.assign(s2)
+        gpflow.set_trainable(m.likelihood.variance, False)
+        m.lml_and_constrained_grads()  # warm the workspaces
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        try:
+            res = gpflow.optimizers.Scipy().minimize(m.training_loss, m.trainable_variables, options=dict(maxiter=100))
+            mean, var = m.predict_f(X)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[tag] = {"fit_predict_s": dt, "nit": int(res.nit), "nfev": int(res.nfev), "ms_per_eval": 1e3 * dt / max(1, res.nfev),
+                        "final_loss": float(res.fun)}
+        except Exception as e:
+            out[tag] = {"error": repr(e)[:200]}
+    out["workload"] = "C1: N=1000, D=1, SE+Periodic(SE), Scipy L-BFGS-B maxiter=100 + predict_f (wall clock, host loop included)"
+    return out
 
 
 def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
