@@ -66,31 +66,47 @@ assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__
     const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(Kout) & 15) == 0);
     const bool diag_tile = (mode != 0) && (ti == tj);
 
+    const bool fastk = (kp.n_leaves <= GRAD_FAST_LEAVES);
 #pragma unroll 1
-    for (int rr = 0; rr < ROWS_PT; ++rr) {
+    for (int rr = 0; rr < ROWS_PT; rr += 2) {
         const int r = ty * ROWS_PT + rr;
-        const int64_t gi = row0 + r;
-        double xi[DP];
+        double xa[DP], xb[DP];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) xi[d] = xs_i[r][d];
-        double v0 = kernel_value<DP>(kp, xi, xj0);
-        double v1 = kernel_value<DP>(kp, xi, xj1);
-        if (diag_tile) {
-            if (r == c0) v0 += diag_add;
-            if (r == c0 + 1) v1 += diag_add;
+        for (int d = 0; d < DP; ++d) {
+            xa[d] = xs_i[r][d];
+            xb[d] = xs_i[r + 1][d];
         }
-        if (mode == 2) {
-            stage[r * TILE + ((c0 + r) & (TILE - 1))] = v0;
-            stage[r * TILE + ((c0 + 1 + r) & (TILE - 1))] = v1;
+        double v[4];   // (r, c0) (r, c0+1) (r+1, c0) (r+1, c0+1)
+        if (fastk) {
+            kernel_value_2x2<DP>(kp, xa, xb, xj0, xj1, v);
+        } else {
+            v[0] = kernel_value<DP>(kp, xa, xj0);
+            v[1] = kernel_value<DP>(kp, xa, xj1);
+            v[2] = kernel_value<DP>(kp, xb, xj0);
+            v[3] = kernel_value<DP>(kp, xb, xj1);
         }
-        if (gi < N) {
-            const int64_t gj = col0 + c0;
-            double* p = Kout + gi * ldk + gj;
-            if (vec_ok && gj + 1 < N2) {
-                *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
-            } else {
-                if (gj < N2) p[0] = v0;
-                if (gj + 1 < N2) p[1] = v1;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int rw = r + h2;
+            const int64_t gi = row0 + rw;
+            double v0 = v[2 * h2], v1 = v[2 * h2 + 1];
+            if (diag_tile) {
+                if (rw == c0) v0 += diag_add;
+                if (rw == c0 + 1) v1 += diag_add;
+            }
+            if (mode == 2) {
+                stage[rw * TILE + ((c0 + rw) & (TILE - 1))] = v0;
+                stage[rw * TILE + ((c0 + 1 + rw) & (TILE - 1))] = v1;
+            }
+            if (gi < N) {
+                const int64_t gj = col0 + c0;
+                double* p = Kout + gi * ldk + gj;
+                if (vec_ok && gj + 1 < N2) {
+                    *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+                } else {
+                    if (gj < N2) p[0] = v0;
+                    if (gj + 1 < N2) p[1] = v1;
+                }
             }
         }
     }

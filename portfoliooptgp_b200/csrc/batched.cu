@@ -10,6 +10,9 @@
 // 8(N D + N) bytes in and 8(2 + P) out; everything else stays on chip.
 //
 // N <= 128 (one 128 x 132 fp64 tile = 135 KB of the 227 KB shared memory), D <= 16.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "block_chol.cuh"
 #include "engine.cuh"
 
@@ -26,21 +29,20 @@ struct BatchedSmem {
     static constexpr int RED = Y + 3 * 128;      // BW x (GPB_MAX_PARAMS + 2)
     static constexpr int MISC = RED + BW * (GPB_MAX_PARAMS + 2);  // scalars
     static constexpr int DINV = MISC + 32;       // inverted 8x8 diagonal blocks
-    static constexpr int KP = DINV + DINV_DOUBLES;  // DevKernel
-    static constexpr int XS = KP + (int)((sizeof(DevKernel) + 7) / 8);  // X tile: 128 x DP
+    static constexpr int XS = DINV + DINV_DOUBLES;  // X tile: 128 x (DP + 1)  (odd stride: 2-way instead of 16-way bank conflicts)
 };
 
 template <int DP>
-constexpr size_t batched_smem_bytes() { return (size_t)(BatchedSmem::XS + 128 * DP + 16) * sizeof(double); }
+constexpr size_t batched_smem_bytes() { return (size_t)(BatchedSmem::XS + 128 * (DP + 1) + 16) * sizeof(double); }
 
 // mode 0: LML only; 1: LML + gradient; 2: predict_f at Ns points per GP
 template <int DP>
 __global__ void __launch_bounds__(BT, 1)
-batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __restrict__ X,
-                  const double* __restrict__ Yc, const double* __restrict__ theta, const double* __restrict__ noise,
+batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kbad, const double* __restrict__ X,
+                  const double* __restrict__ Yc, const double* __restrict__ noise,
                   int N, int D, int mode, double* __restrict__ out, int* __restrict__ info,
                   const double* __restrict__ Xs_new, int Ns, double* __restrict__ mean_out,
-                  double* __restrict__ var_out) {
+                  double* __restrict__ var_out, long long* __restrict__ prof) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm + BatchedSmem::S;
     double* T = sm + BatchedSmem::T;
@@ -51,62 +53,72 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
     double* misc = sm + BatchedSmem::MISC;
     double* dinv = sm + BatchedSmem::DINV;
     int* fail = reinterpret_cast<int*>(misc + 8);
-    DevKernel& kp = *reinterpret_cast<DevKernel*>(sm + BatchedSmem::KP);
-    double* xs = sm + BatchedSmem::XS;  // [128][DP]
+    double* xs = sm + BatchedSmem::XS;  // [128][XSTR]
+    constexpr int XSTR = DP + 1;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int np = (N + 7) & ~7;
-    const int P = spec.n_params;
+    // per-GP kernel descriptor, built by build_dev_kernels_kernel; read-only global memory (not shared
+    // memory) so that the compiler may keep its loop-invariant fields in registers
+    const DevKernel& kp = kps[b];
+    const int P = kp.n_params;
     const double* Xb = X + (size_t)b * N * D;
-    const double* th = theta + (size_t)b * P;
 
-    if (tid == 0) {
-        int bad = build_dev_kernel_core(spec, th, &kp);
-        misc[9] = (double)bad;
-    }
+    const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && tid == 0;
+    if (do_prof) prof[0] = clock64();
+    if (tid == 0) misc[9] = (double)kbad[b];
     for (int e = tid; e < 128 * DP; e += BT) {
         const int r = e / DP, d = e % DP;
-        xs[e] = (r < N && d < D) ? Xb[r * D + d] : 0.0;
+        xs[r * XSTR + d] = (r < N && d < D) ? Xb[r * D + d] : 0.0;
     }
     if (tid < 128) ys[tid] = (tid < N) ? Yc[(size_t)b * N + tid] : 0.0;
     __syncthreads();
     const double nv = noise[b];
+    if (do_prof) prof[1] = clock64();
 
-    // ---- assembly: 8x8 tiles of the lower triangle, fragment layout of the DMMA C tile
+    // ---- assembly: 2 x 2 blocks of the lower triangle, four elements advance together (kernel_value_2x2)
     const int nt8 = np >> 3;
     {
-        for (int t = warp; t < nt8 * (nt8 + 1) / 2; t += BW) {
-            {
-                int ti, tj;
-                tri_tile(t, ti, tj);
-                const int i = ti * 8 + g, j0 = tj * 8 + 2 * q;
-                double xi[DP], xj[DP];
+        const int nb2 = np >> 1;
+        const bool fastk = (kp.n_leaves <= GRAD_FAST_LEAVES);
+        for (int t = tid; t < nb2 * (nb2 + 1) / 2; t += BT) {
+            int bi, bj;
+            tri_tile(t, bi, bj);
+            const int i0 = 2 * bi, j0 = 2 * bj;
+            double xa[DP], xb[DP], xj0[DP], xj1[DP];
 #pragma unroll
-                for (int d = 0; d < DP; ++d) xi[d] = xs[i * DP + d];
-                double v[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int j = j0 + c;
-#pragma unroll
-                    for (int d = 0; d < DP; ++d) xj[d] = xs[j * DP + d];
-                    double val;
-                    if (i < N && j < N) {
-                        val = kernel_value<DP>(kp, xi, xj);
-                        if (i == j) val += nv;
-                    } else {
-                        val = (i == j) ? 1.0 : 0.0;  // identity padding
-                    }
-                    v[c] = val;
-                }
-                *reinterpret_cast<double2*>(S + i * SLD + j0) = make_double2(v[0], v[1]);
+            for (int d = 0; d < DP; ++d) {
+                xa[d] = xs[i0 * XSTR + d];
+                xb[d] = xs[(i0 + 1) * XSTR + d];
+                xj0[d] = xs[j0 * XSTR + d];
+                xj1[d] = xs[(j0 + 1) * XSTR + d];
             }
+            double v[4];
+            if (fastk) {
+                kernel_value_2x2<DP>(kp, xa, xb, xj0, xj1, v);
+            } else {
+                v[0] = kernel_value<DP>(kp, xa, xj0);
+                v[1] = kernel_value<DP>(kp, xa, xj1);
+                v[2] = kernel_value<DP>(kp, xb, xj0);
+                v[3] = kernel_value<DP>(kp, xb, xj1);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + (e >> 1), j = j0 + (e & 1);
+                if (i >= N || j >= N) v[e] = (i == j) ? 1.0 : 0.0;   // identity padding
+                else if (i == j) v[e] += nv;
+            }
+            *reinterpret_cast<double2*>(S + i0 * SLD + j0) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(S + (i0 + 1) * SLD + j0) = make_double2(v[2], v[3]);
         }
     }
     __syncthreads();
+    if (do_prof) prof[2] = clock64();
 
     block_potrf_lower(S, np, fail, dinv);
+    if (do_prof) prof[3] = clock64();
     // log-det (fixed order) by warp 0
     if (warp == 0) {
         double s = 0.0;
@@ -117,6 +129,7 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
     }
     __syncthreads();
     block_trtri_lower_inplace(S, np, T, dinv);   // S <- W = L^-1
+    if (do_prof) prof[4] = clock64();
 
     // ---- a = W y (warp per row), alpha = W^T a (thread per column)
     for (int i = warp; i < np; i += BW) {
@@ -141,6 +154,7 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
     }
     __syncthreads();
 
+    if (do_prof) prof[5] = clock64();
     if (mode == 2) {
         // predict_f: mean_s = k_s^T alpha ; var_s = k_ss - |W k_s|^2.  One warp per test point.
         double* ks = T;  // BW x 128 scratch
@@ -152,8 +166,8 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
             for (int i = lane; i < np; i += 32) {
                 double xi[DP];
 #pragma unroll
-                for (int d = 0; d < DP; ++d) xi[d] = xs[i * DP + d];
-                const double kv = (i < N) ? kernel_value<DP>(kp, xi, xn) : 0.0;
+                for (int d = 0; d < DP; ++d) xi[d] = xs[i * XSTR + d];
+                const double kv = (i < N) ? kernel_value_auto<DP>(kp, xi, xn) : 0.0;
                 ks[warp * 128 + i] = kv;
                 m = fma(kv, als[i], m);
             }
@@ -199,7 +213,7 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
                 if (i < N) {
                     double xi[DP], xj[DP];
 #pragma unroll
-                    for (int d = 0; d < DP; ++d) xi[d] = xs[i * DP + d];
+                    for (int d = 0; d < DP; ++d) xi[d] = xs[i * XSTR + d];
                     const double ai = als[i];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -208,7 +222,7 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
                             double w = ai * als[j] - (c == 0 ? c0 : c1);
                             if (j == i) tr += w; else w *= 2.0;
 #pragma unroll
-                            for (int d = 0; d < DP; ++d) xj[d] = xs[j * DP + d];
+                            for (int d = 0; d < DP; ++d) xj[d] = xs[j * XSTR + d];
                             if (fast) kernel_value_grad_fast<DP>(kp, xi, xj, w, A);
                             else kernel_value_grad<DP>(kp, xi, xj, w, acc);
                         }
@@ -241,10 +255,19 @@ batched_gp_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __
             if (tid == P) o[1] = 0.5 * v; else o[2 + tid] = 0.5 * v;
         }
     }
+    if (do_prof) prof[6] = clock64();
     if (tid == 0) {
         o[0] = -0.5 * misc[11] - 0.5 * (double)N * 1.8378770664093453 - misc[10];   // log(2 pi)
         info[b] = (misc[9] != 0.0) ? -(int)misc[9] : *fail;
     }
+}
+
+// one thread per GP: spec + theta[b] -> DevKernel[b]
+__global__ void build_dev_kernels_kernel(const __grid_constant__ gpb_kernel_spec spec, const double* __restrict__ theta,
+                                         int64_t B, DevKernel* __restrict__ out, int* __restrict__ bad) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    bad[b] = build_dev_kernel_core(spec, theta + b * spec.n_params, out + b);
 }
 
 template <int DP>
@@ -259,9 +282,32 @@ static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Y
         if (e != cudaSuccess) return check_cuda(h, e, "batched cudaFuncSetAttribute");
         attr_set = true;
     }
-    ProfScope prof(h, PROF_BATCHED, h->stream);
-    kern<<<(unsigned)B, BT, SMEM, h->stream>>>(h->spec, d_X, d_Yc, d_theta, d_noise, N, D, mode, d_out, d_info, d_Xs, Ns,
-                                                d_mean, d_var);
+    static long long* d_prof = nullptr;   // GPB_BATCHED_PROF=1: phase cycle stamps of CTA 0 to stderr (debug)
+    static int want_prof = -1;
+    if (want_prof < 0) {
+        const char* e = getenv("GPB_BATCHED_PROF");
+        want_prof = (e && e[0] == '1') ? 1 : 0;
+        if (want_prof) cudaMalloc(&d_prof, 8 * sizeof(long long));
+    }
+    const size_t kbytes = ((size_t)B * sizeof(DevKernel) + 255) / 256 * 256;
+    double* kbuf = workspace(h, BUF_AUX, kbytes + (size_t)B * sizeof(int));
+    if (!kbuf) return -1;
+    DevKernel* kps = reinterpret_cast<DevKernel*>(kbuf);
+    int* kbad = reinterpret_cast<int*>(reinterpret_cast<char*>(kbuf) + kbytes);
+    {
+        ProfScope prof(h, PROF_BATCHED, h->stream);
+        build_dev_kernels_kernel<<<(unsigned)((B + 127) / 128), 128, 0, h->stream>>>(h->spec, d_theta, B, kps, kbad);
+        kern<<<(unsigned)B, BT, SMEM, h->stream>>>(kps, kbad, d_X, d_Yc, d_noise, N, D, mode, d_out, d_info, d_Xs, Ns,
+                                                    d_mean, d_var, want_prof ? d_prof : nullptr);
+        h->launches += 1;
+    }
+    if (want_prof && d_prof) {
+        long long st[8];
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(st, d_prof, sizeof(st), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[batched prof, cycles] setup %lld assemble %lld potrf %lld trtri %lld vectors %lld grad/predict %lld total %lld\n",
+                st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[6] - st[5], st[6] - st[0]);
+    }
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "batched_gp_kernel launch");
 }

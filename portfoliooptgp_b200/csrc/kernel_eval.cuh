@@ -20,6 +20,57 @@
 
 namespace gpb {
 
+// ---- exp for the kernel evaluations ---------------------------------------------------------------
+// exp(x) = 2^k * P(r), k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite), P = degree-13 Taylor
+// polynomial on |r| <= ln2 / 2 (truncation 4e-18, total error about 1 ulp).  The library exp()
+// materialises every coefficient with two UMOVs per use and is issue-bound (50 instructions for 15
+// FP64 ones); here the coefficients come from the constant bank and a vector of V independent
+// arguments shares each coefficient load, which makes the evaluation FP64-pipe-bound.
+// Gradual underflow below 2^-1000 is handled by a second scaling; x < -750 returns 0.
+static __constant__ double GPB_EXPC[14] = {1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02,
+                                    8.333333333333333e-03, 1.388888888888889e-03, 1.984126984126984e-04,
+                                    2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07,
+                                    2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10};
+static __constant__ double GPB_EXPK[4] = {1.4426950408889634, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+                                   6755399441055744.0};
+
+template <int V>
+__device__ __forceinline__ void exp_vec(double (&x)[V]) {
+    double r[V], p[V];
+    int k[V];
+    const double l2e = GPB_EXPK[0], ln2h = GPB_EXPK[1], ln2l = GPB_EXPK[2], magic = GPB_EXPK[3];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const double t = fma(x[v], l2e, magic);
+        k[v] = __double2loint(t);
+        const double n = t - magic;
+        r[v] = fma(n, -ln2l, fma(n, -ln2h, x[v]));
+        p[v] = GPB_EXPC[13];
+    }
+#pragma unroll
+    for (int i = 12; i >= 0; --i) {
+        const double c = GPB_EXPC[i];
+#pragma unroll
+        for (int v = 0; v < V; ++v) p[v] = fma(p[v], r[v], c);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int k1 = max(k[v], -1000);
+        double res = p[v] * __hiloint2double((k1 + 1023) << 20, 0);
+        if (k[v] != k1) res = (x[v] < -750.0) ? 0.0 : res * __hiloint2double((max(k[v] - k1, -200) + 1023) << 20, 0);
+        x[v] = res;
+    }
+}
+
+__device__ __forceinline__ double gpb_exp(double x) {
+    return exp(x);   // scalar paths: the library exp (immediates) measured faster than constant-bank loads here
+}
+__device__ __forceinline__ double gpb_exp_cb(double x) {
+    double a[1] = {x};
+    exp_vec<1>(a);
+    return a[0];
+}
+
 struct DevGroup {
     int kind;
     int ard_index;     // theta index of first ARD lengthscale, or -1
@@ -184,13 +235,13 @@ __device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
             f = u; fp_u = u; fp = 1.0;
         } break;
         case GPB_LEAF_SE: {
-            f = exp(-0.5 * u);
+            f = gpb_exp(-0.5 * u);
             fp = -0.5 * f; fp_u = fp * u;
         } break;
         case GPB_LEAF_RQ: {
             const double b = 1.0 + 0.5 * u / lf.alpha;
             const double lb = log(b);
-            f = exp(-lf.alpha * lb);
+            f = gpb_exp(-lf.alpha * lb);
             fp = -0.5 * f / b; fp_u = fp * u;
             if (GRAD) o.dv_dalpha = lf.variance * f * (-lb + 0.5 * u / (lf.alpha * b));
         } break;
@@ -200,16 +251,16 @@ __device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
             const double r = lf.arg_is_r ? u : sqrt(fmax(u, 1e-36));
             double df_dr;  // f'(r)
             if (lf.kind == GPB_LEAF_MATERN12) {
-                f = exp(-r); df_dr = -f;
+                f = gpb_exp(-r); df_dr = -f;
             } else if (lf.kind == GPB_LEAF_EXPONENTIAL) {
-                f = exp(-0.5 * r); df_dr = -0.5 * f;
+                f = gpb_exp(-0.5 * r); df_dr = -0.5 * f;
             } else if (lf.kind == GPB_LEAF_MATERN32) {
                 const double s3 = 1.7320508075688772;
-                const double e = exp(-s3 * r);
+                const double e = gpb_exp(-s3 * r);
                 f = (1.0 + s3 * r) * e; df_dr = -3.0 * r * e;
             } else {  // MATERN52
                 const double s5 = 2.23606797749979;
-                const double e = exp(-s5 * r);
+                const double e = gpb_exp(-s5 * r);
                 f = (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
                 df_dr = -(5.0 / 3.0) * r * (1.0 + s5 * r) * e;
             }
@@ -344,6 +395,134 @@ __device__ __forceinline__ double sel4(const double (&a)[GRAD_FAST_LEAVES], int 
 #pragma unroll
     for (int l = 1; l < GRAD_FAST_LEAVES; ++l) r = (id == l) ? a[l] : r;
     return r;
+}
+
+// Forward value with the leaves statically unrolled (same structure as the gradient fast path): the
+// per-leaf constants sit at compile-time offsets of the kernel-parameter block, so the compiler
+// hoists them out of the element loops instead of chasing term -> leaf -> group indices per element.
+template <int DP>
+__device__ __forceinline__ double kernel_value_fast(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP]) {
+    double v[GRAD_FAST_LEAVES];
+    double s_prev = 0.0;
+    int g_prev = -1;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        v[l] = 0.0;
+        if (l < kp.n_leaves) {
+            const DevLeaf& lf = kp.leaves[l];
+            if (lf.group != g_prev) {
+                double dummy;
+                s_prev = group_value<DP, false>(kp.groups[lf.group], xi, xj, dummy);
+                g_prev = lf.group;
+            }
+            v[l] = leaf_value<false>(lf, s_prev).v;
+        }
+    }
+    double total = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        double prod = sel4(v, tm.leaf[0]);
+#pragma unroll
+        for (int f = 1; f < GPB_MAX_FACTORS; ++f)
+            if (f < tm.n_factors) prod *= sel4(v, tm.leaf[f]);
+        total += prod;
+    }
+    return total;
+}
+
+// Vectorised leaf: v[e] = variance * f(s[e] * scale) for V elements at once (uniform switch outside,
+// the exponentials of all V elements share the coefficient loads through exp_vec).
+template <int V>
+__device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (&s)[V], double (&v)[V]) {
+    double a[V];
+    switch (lf.kind) {
+        case GPB_LEAF_LINEAR: {
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = lf.variance * (s[e] * lf.scale);
+        } break;
+        case GPB_LEAF_SE: {
+#pragma unroll
+            for (int e = 0; e < V; ++e) a[e] = -0.5 * (s[e] * lf.scale);
+            exp_vec<V>(a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = lf.variance * a[e];
+        } break;
+        case GPB_LEAF_RQ: {
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = leaf_value<false>(lf, s[e]).v;
+        } break;
+        default: {
+            double r[V];
+            const double c = (lf.kind == GPB_LEAF_MATERN12) ? 1.0
+                             : (lf.kind == GPB_LEAF_EXPONENTIAL) ? 0.5
+                             : (lf.kind == GPB_LEAF_MATERN32) ? 1.7320508075688772 : 2.23606797749979;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const double u = s[e] * lf.scale;
+                r[e] = lf.arg_is_r ? u : sqrt(fmax(u, 1e-36));
+                a[e] = -c * r[e];
+            }
+            exp_vec<V>(a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                double poly = 1.0;
+                if (lf.kind == GPB_LEAF_MATERN32) poly = 1.0 + c * r[e];
+                else if (lf.kind == GPB_LEAF_MATERN52) poly = 1.0 + c * r[e] + (5.0 / 3.0) * r[e] * r[e];
+                v[e] = lf.variance * (poly * a[e]);
+            }
+        } break;
+    }
+}
+
+// k for the 2 x 2 block {xa, xb} x {xj0, xj1}: out = {k(xa,xj0), k(xa,xj1), k(xb,xj0), k(xb,xj1)}.
+// Same arithmetic per element as kernel_value_fast; four elements advance together.
+template <int DP>
+__device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const double (&xa)[DP], const double (&xb)[DP],
+                                                 const double (&xj0)[DP], const double (&xj1)[DP], double (&out)[4]) {
+    double v[GRAD_FAST_LEAVES][4];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int g_prev = -1;
+#pragma unroll
+    for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[l][e] = 0.0;
+        if (l < kp.n_leaves) {
+            const DevLeaf& lf = kp.leaves[l];
+            if (lf.group != g_prev) {
+                double dummy;
+                const DevGroup& g = kp.groups[lf.group];
+                s[0] = group_value<DP, false>(g, xa, xj0, dummy);
+                s[1] = group_value<DP, false>(g, xa, xj1, dummy);
+                s[2] = group_value<DP, false>(g, xb, xj0, dummy);
+                s[3] = group_value<DP, false>(g, xb, xj1, dummy);
+                g_prev = lf.group;
+            }
+            leaf_value_vec<4>(lf, s, v[l]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = 0.0;
+    for (int t = 0; t < kp.n_terms; ++t) {
+        const DevTerm& tm = kp.terms[t];
+        double prod[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) prod[e] = 1.0;
+#pragma unroll
+        for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+            if (f < tm.n_factors) {
+                const int id = tm.leaf[f];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double fv = v[0][e];
+#pragma unroll
+                    for (int l = 1; l < GRAD_FAST_LEAVES; ++l) fv = (id == l) ? v[l][e] : fv;
+                    prod[e] *= fv;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] += prod[e];
+    }
 }
 
 template <int DP>
@@ -549,6 +728,12 @@ __device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, doub
             if (pi >= 0) out[pi] += d;
         }
     }
+}
+
+// dispatch: statically unrolled path when the expression has <= GRAD_FAST_LEAVES leaves
+template <int DP>
+__device__ __forceinline__ double kernel_value_auto(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP]) {
+    return (kp.n_leaves <= GRAD_FAST_LEAVES) ? kernel_value_fast<DP>(kp, xi, xj) : kernel_value<DP>(kp, xi, xj);
 }
 
 // k(x, x) on the diagonal (gpflow K_diag): stationary -> variance, Linear -> sum w_d x_d^2.
