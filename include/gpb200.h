@@ -160,6 +160,11 @@ int gpb_gpr_lml_grad(gpb_handle* h, const double* h_theta, double noise_variance
 int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Xs,
                       int64_t Ns, double* d_mean, double* d_var);
 
+/* d_alpha [N] <- (K + noise I)^-1 (Y - m(X)) of the last gpb_gpr_lml / gpb_gpr_lml_grad / gpb_gpr_predict_f
+ * evaluation on this handle (= dLML/dm(X); lets the host layer train mean-function parameters,
+ * test_scripts/GPFlow.py:186-190 uses Constant / Linear mean functions).  Asynchronous. */
+int gpb_gpr_get_alpha(gpb_handle* h, double* d_alpha);
+
 /* ---- batched independent small GPs (north_star subsystem 4) -------------------------------------
  * One GP per CTA, K resident in shared memory (N <= 128).  Replaces the sequential rolling re-fit
  * loop Multi-Input_GPR/main.py:414-456 x restarts models/model_trainer.py:26-48: B independent

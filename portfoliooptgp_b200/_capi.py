@@ -85,6 +85,7 @@ SIGNATURES = {
     "gpb_gpr_lml": (_INT, [_P, _DP, _D, _DP]),
     "gpb_gpr_lml_grad": (_INT, [_P, _DP, _D, _DP, _DP, _DP]),
     "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
+    "gpb_gpr_get_alpha": (_INT, [_P, _P]),
     "gpb_batched_lml_grad": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
     "gpb_batched_predict_f": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
     "gpb_svgp_flat_size": (_I64, [_I64, _INT, _INT]),
@@ -271,3 +272,6 @@ class Engine:
                   eps=1e-8, maximize: bool = True):
         self._check(self._lib.gpb_adam_step(self._h, _P(dx), _P(dg), _P(dm), _P(dv), n, float(lr), float(beta1),
                                             float(beta2), float(eps), int(step), int(bool(maximize))), "gpb_adam_step")
+
+    def gpr_get_alpha(self, dalpha: int):
+        self._check(self._lib.gpb_gpr_get_alpha(self._h, _P(dalpha)), "gpb_gpr_get_alpha")

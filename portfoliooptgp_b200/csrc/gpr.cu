@@ -144,3 +144,26 @@ int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double
 }
 
 }  // namespace gpb
+
+namespace gpb {
+
+// alpha = (K + noise I)^-1 (y - m(X)) of the LAST gpr_lml / gpr_predict_f evaluation on this handle
+// (= d LML / d m(X): what the host layer needs to train mean-function parameters).
+int gpr_get_alpha(gpb_handle* h, double* d_alpha) {
+    if (!h->d_X || h->N <= 0) return set_error(h, -3, "get_alpha: no data bound");
+    GprWork w;
+    int rc = gpr_workspaces(h, &w);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(d_alpha, w.alpha, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    return check_cuda(h, e, "get_alpha copy");
+}
+
+}  // namespace gpb
+
+extern "C" int gpb_gpr_get_alpha(gpb_handle* h, double* d_alpha) {
+    if (!h) return -1;
+    cudaError_t e_ = cudaSetDevice(h->device);
+    if (e_ != cudaSuccess) return gpb::check_cuda(h, e_, "cudaSetDevice");
+    if (!d_alpha) return gpb::set_error(h, -2, "get_alpha: null pointer");
+    return gpb::gpr_get_alpha(h, d_alpha);
+}

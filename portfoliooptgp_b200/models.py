@@ -206,7 +206,11 @@ class GPR(GPModel):
         pv = self.likelihood.variance
         by_param[id(pv)] = np.asarray(g_noise) * pv.transform.forward_grad(pv.unconstrained_variable._value)
         if any(p.trainable for p in self.mean_function.parameters):
-            raise NotImplementedError("trainable mean-function parameters are not supported yet")
+            # dLML/dm(X) = alpha = (K + s2 I)^-1 (Y - m(X)); chain rule through the mean function on the device
+            Xd = self.data[0]
+            alpha = torch.empty(Xd.shape[0], dtype=torch.float64, device=Xd.device)
+            eng.gpr_get_alpha(alpha.data_ptr())
+            by_param.update(self.mean_function.backward(Xd, alpha))
         return -lml, self._grads_for(variables, by_param, -1.0)
 
     # -- prediction ----------------------------------------------------------------------------

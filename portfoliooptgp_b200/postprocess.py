@@ -1,0 +1,67 @@
+"""Prediction post-processing of the reference's Predictor (GPR/predictor.py:10-51):
+linear-interpolation upsampling of the weekly / monthly predictions onto the daily grid and the
+alpha / beta blend of the three time frames.  O(N*) host arithmetic on the [N*,1] outputs of
+predict_f / predict_y; kept out of the device path on purpose (a few hundred values)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _np(a):
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    elif hasattr(a, "numpy") and not isinstance(a, np.ndarray):
+        a = a.numpy()
+    return np.asarray(a, dtype=np.float64)
+
+
+def upsample_predictions(X_daily, X, predictions, period: str = "d"):
+    """GPR/predictor.py:35-51: ``pd.Series(pred, index=X).reindex(X_daily).interpolate('linear')``.
+    pandas' 'linear' ignores the index and interpolates over POSITIONS in the daily grid; leading
+    gaps stay NaN, trailing gaps repeat the last value."""
+    if period not in ("w", "m"):
+        return predictions
+    xd = _np(X_daily).reshape(-1)
+    x = _np(X).reshape(-1)
+    p = _np(predictions).reshape(-1)
+    lookup = {}
+    for xi, pi in zip(x, p):
+        lookup.setdefault(xi, pi)   # reindex on a unique index; duplicates are not produced by the reference
+    vals = np.array([lookup.get(v, np.nan) for v in xd], dtype=np.float64)
+    pos = np.arange(len(xd), dtype=np.float64)
+    ok = ~np.isnan(vals)
+    out = vals.copy()
+    if ok.any():
+        first, last = np.argmax(ok), len(ok) - 1 - np.argmax(ok[::-1])
+        inner = slice(first, last + 1)
+        out[inner] = np.interp(pos[inner], pos[ok], vals[ok])
+        out[last + 1:] = vals[last]
+    return out.reshape(-1, 1)
+
+
+def predict_combined(alpha, beta, daily, weekly, monthly, X_daily, X_weekly, X_monthly):
+    """GPR/predictor.py:10-33.  ``daily`` / ``weekly`` / ``monthly`` are the 4-tuples
+    (f_mean, f_var, y_mean, y_var) of Predictor.predict_single for each model."""
+    out = []
+    for d, w, m in zip(daily, weekly, monthly):
+        wu = upsample_predictions(X_daily, X_weekly, w, period="w")
+        mu = upsample_predictions(X_daily, X_monthly, m, period="m")
+        out.append(alpha * _np(d) + beta * wu + (1 - alpha - beta) * mu)
+    return tuple(out)
+
+
+class Predictor:
+    """Drop-in for GPR/predictor.py's class (same method names and argument order)."""
+
+    def predict_single(self, model, X):
+        f_mean, f_var = model.predict_f(X, full_cov=False)
+        y_mean, y_var = model.predict_y(X)
+        return f_mean, f_var, y_mean, y_var
+
+    def predict_combined(self, alpha, beta, daily_model, weekly_model, monthly_model, X_daily, X_weekly, X_monthly):
+        return predict_combined(alpha, beta, self.predict_single(daily_model, X_daily),
+                                self.predict_single(weekly_model, X_weekly), self.predict_single(monthly_model, X_monthly),
+                                X_daily, X_weekly, X_monthly)
+
+    def upsample_predictions(self, X_daily, X, predictions, period="d"):
+        return upsample_predictions(X_daily, X, predictions, period)

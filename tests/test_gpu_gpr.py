@@ -120,3 +120,44 @@ def test_non_pd_raises(gp):
     m2 = gp.models.GPR((X2, Y), kernel=gp.kernels.Linear(), noise_variance=2e-6)
     with pytest.raises(gp.CholeskyError):
         float(m2.log_marginal_likelihood())
+
+
+def test_mean_functions_train_and_predict(gp):
+    """Constant / Linear / Polynomial(2) mean functions (test_scripts/GPFlow.py:186-190, GPR.py:103):
+    LML and gradients w.r.t. the mean parameters against the oracle (mean enters only through Y - m(X))."""
+    X, Y = make_multi_input(61, 150, 1)
+    Y = Y + 0.7 * X + 0.3                     # give the mean something to explain
+    noise = 1e-2
+    k = gp.kernels.SquaredExponential(lengthscales=0.7)
+    ko = to_oracle(k)
+    for mf, m_of_x, dparams in [
+        (gp.mean_functions.Constant(0.2), lambda X: 0.2 + 0 * X, lambda a, X: [a.sum()]),
+        (gp.mean_functions.Linear(np.array([[0.5]]), np.array([0.1])), lambda X: 0.5 * X + 0.1,
+         lambda a, X: [(a * X[:, 0]).sum(), a.sum()]),
+        (gp.mean_functions.Polynomial(2, w=[0.1, 0.4, -0.05]), lambda X: 0.1 + 0.4 * X - 0.05 * X ** 2,
+         lambda a, X: [a.sum(), (a * X[:, 0]).sum(), (a * X[:, 0] ** 2).sum()]),
+    ]:
+        m = gp.models.GPR((X, Y), kernel=k, mean_function=mf, noise_variance=noise)
+        resid = Y - m_of_x(X)
+        l0 = O.gpr_lml(ko, X, resid, noise)
+        assert abs(float(m.log_marginal_likelihood()) - l0) <= 1e-9 * abs(l0)
+        L = O.gpr_cholesky(ko, X, noise)
+        import scipy.linalg as sla
+        alpha = sla.cho_solve((L, True), resid)[:, 0]
+        variables = m.trainable_variables
+        loss, grads = m.training_loss_closure().value_and_grads(variables)
+        by_var = {id(v): g for v, g in zip(variables, grads)}
+        got = np.concatenate([-by_var[id(p.unconstrained_variable)].reshape(-1) for p in mf.parameters])
+        want = np.array(dparams(alpha, X), dtype=np.float64)
+        assert np.max(np.abs(got - want)) <= 1e-7 * max(1.0, np.max(np.abs(want)))
+        # predict_f adds the mean back
+        Xs = np.linspace(-1, 1, 7)[:, None]
+        mean, _ = m.predict_f(Xs)
+        m0, _ = O.gpr_predict_f(ko, X, resid, noise, Xs)
+        assert np.max(np.abs(mean.numpy() - (m0 + m_of_x(Xs)))) <= 1e-9 * max(1.0, np.max(np.abs(m0)))
+    # and the optimiser can train them
+    mf = gp.mean_functions.Linear()
+    m = gp.models.GPR((X, Y), kernel=gp.kernels.SquaredExponential(), mean_function=mf, noise_variance=noise)
+    before = float(m.training_loss())
+    res = gp.optimizers.Scipy().minimize(m.training_loss, m.trainable_variables, options=dict(maxiter=30))
+    assert res.fun < before
