@@ -41,10 +41,13 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
     const double l2e = GPB_EXPK[0], ln2h = GPB_EXPK[1], ln2l = GPB_EXPK[2], magic = GPB_EXPK[3];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const double t = fma(x[v], l2e, magic);
+        // the rint-by-magic-constant trick needs |x log2 e| < 2^31: clamp to the range where exp is finite
+        // and non-zero (trial points of the line search can make r^2 / l^2 astronomically large)
+        const double xc = fmin(fmax(x[v], -760.0), 709.0);
+        const double t = fma(xc, l2e, magic);
         k[v] = __double2loint(t);
         const double n = t - magic;
-        r[v] = fma(n, -ln2l, fma(n, -ln2h, x[v]));
+        r[v] = fma(n, -ln2l, fma(n, -ln2h, xc));
         p[v] = GPB_EXPC[13];
     }
 #pragma unroll
@@ -58,7 +61,7 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
         const int k1 = max(k[v], -1000);
         double res = p[v] * __hiloint2double((k1 + 1023) << 20, 0);
         if (k[v] != k1) res = (x[v] < -750.0) ? 0.0 : res * __hiloint2double((max(k[v] - k1, -200) + 1023) << 20, 0);
-        x[v] = res;
+        x[v] = (x[v] != x[v]) ? x[v] : res;   // NaN in, NaN out
     }
 }
 

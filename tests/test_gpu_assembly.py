@@ -50,3 +50,27 @@ def test_gram_form_gap_is_small(gp):
     assert np.max(np.abs(got - ref)) < 1e-7  # Matern r = sqrt(r2) amplifies Gram cancellation near r = 0
     off = ~np.eye(200, dtype=bool)
     assert np.max(np.abs(got - ref)[off]) < 1e-12
+
+
+def test_extreme_hyperparameters_stay_finite(gp):
+    """Line-search trial points reach absurd lengthscales (SciPy L-BFGS-B on the C1 workload visits
+    l ~ 1e-8): exp arguments of -1e13 must give exactly 0, not garbage; the gradual-underflow window
+    [-745, -708] must match numpy."""
+    from portfoliooptgp_b200 import ops
+    X, _ = make_multi_input(13, 300, 2)
+    for ls in (1e-8, 1e-3, 1e3, 1e8):
+        k = gp.kernels.SquaredExponential(variance=2.0, lengthscales=ls) + gp.kernels.Periodic(
+            gp.kernels.SquaredExponential(lengthscales=ls * 3, active_dims=[1]), period=1.3)
+        got = ops.kernel_matrix(k, X).cpu().numpy()
+        want = O.K(to_oracle(k), X)
+        assert np.all(np.isfinite(got))
+        assert np.max(np.abs(got - want)) < 1e-12
+    x = np.linspace(0.0, 1.0, 64)[:, None]
+    ls = 1.0 / np.sqrt(2 * 745.0)          # -r^2 / (2 l^2) spans [0, -745]
+    k = gp.kernels.SquaredExponential(lengthscales=ls)
+    got = ops.kernel_matrix(k, x).cpu().numpy()
+    want = O.K(to_oracle(k), x)
+    # (the oracle scales by 1/l before subtracting: its own cancellation error is ~|x/l| eps ~ 5e-15 here)
+    assert np.all(np.isfinite(got)) and np.max(np.abs(got - want)) < 1e-13
+    tiny = want < 1e-290
+    assert np.allclose(got[tiny], want[tiny], rtol=1e-6, atol=1e-320)
