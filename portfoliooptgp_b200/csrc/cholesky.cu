@@ -28,7 +28,7 @@ constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + DINV_DOUBLES + 16) *
 // (block_chol.cuh).  Blocks narrower than 128 are padded to a multiple of 8 with an identity.
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ W, int64_t ldw, int n, int offset,
-                      double* __restrict__ logdiag, int* __restrict__ info) {
+                      double* __restrict__ logdiag, int* __restrict__ info, int store_L) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* T = sm + NB * SLD;
@@ -55,10 +55,14 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     __syncthreads();
     block_potrf_lower(S, np, fail, dinv);
     if (tid == 0 && *fail != 0) atomicCAS(info, 0, offset + *fail);
+    // L itself is only needed by callers that keep the factor (gpb_potrf, SVGP adjoint); the LML / K^-1
+    // pipeline consumes W and the log-diagonal only, so the 128 KB store is skipped there
+    if (store_L) {
 #pragma unroll 8
-    for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
-        const int i = idx >> 7, j = idx & (NB - 1);
-        if (j < n) A[(int64_t)i * lda + j] = S[i * SLD + j];
+        for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
+            const int i = idx >> 7, j = idx & (NB - 1);
+            if (j < n) A[(int64_t)i * lda + j] = S[i * SLD + j];
+        }
     }
     // sum of log-diagonal, fixed order: warp 0
     if (tid < 32) {
@@ -78,7 +82,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
 }
 
 static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int n, int offset, double* logdiag,
-                int* info) {
+                int* info, bool store_L) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(leaf_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
@@ -88,7 +92,7 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
     ProfScope prof(h, PROF_LEAF, h->stream);
     leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A + (int64_t)offset * lda + offset, lda,
                                                                      W + (int64_t)offset * ldw + offset, ldw, n, offset,
-                                                                     logdiag, info);
+                                                                     logdiag, info, store_L ? 1 : 0);
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "leaf_potrf_inv_kernel launch");
 }
@@ -97,7 +101,7 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
 // (needs U scratch of n2 x n1 doubles).
 static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
                           int* info, bool keepL, double* scratchU, int depth) {
-    if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info);
+    if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info, keepL);
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1, o2 = o + n1;
     int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1);
     if (rc) return rc;
@@ -113,7 +117,7 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
     g.A = A21; g.lda = lda; g.B = W11; g.ldb = ldw; g.C = W21; g.ldc = ldw; g.b_upper = 1;
     if ((rc = launch_gemm(h, g, h->stream))) return rc;
     // fork point: everything that only needs T (and W11) may start now
-    const bool fork = h->fork_streams && (depth < gpb_handle::MAX_DEPTH) && h->side[depth] && n2 >= 2 * NB;
+    const bool fork = h->fork_streams && (depth < gpb_handle::MAX_DEPTH) && h->side[depth] && n2 >= NB;
     cudaStream_t us = fork ? h->side[depth] : h->stream;
     if (fork) {
         cudaError_t e = cudaEventRecord(h->ev_fork[depth], h->stream);
