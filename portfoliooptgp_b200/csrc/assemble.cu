@@ -149,8 +149,8 @@ __global__ void kdiag_kernel(const __grid_constant__ DevKernel kp, const double*
 // partial[b][P] = sum over diagonal elements of (alpha_i^2 - Kinv_ii).   dK/dtheta is recomputed from
 // the X tiles and never written.  HBM bytes: one read of the lower triangle of
 // Kinv (8 N(N+1)/2).
-template <int DP>
-__global__ void __launch_bounds__(ASM_THREADS)
+template <int DP, bool FAST>
+__global__ void __launch_bounds__(ASM_THREADS, FAST ? 2 : 1)
 grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N, int D,
                    const double* __restrict__ Kinv, int64_t ldk, const double* __restrict__ alpha,
                    double* __restrict__ partial) {
@@ -176,11 +176,11 @@ grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restric
     __syncthreads();
 
     const int P = kp.n_params;
-    const bool fast = grad_fast_ok(kp);   // register accumulators (every reference kernel) vs generic path
+    constexpr bool fast = FAST;   // register accumulators (every reference kernel) vs generic path: two kernels
     GradAcc A;
     A.zero();
     double tr = 0.0;
-    double acc[GPB_MAX_PARAMS + 1];
+    double acc[FAST ? 1 : GPB_MAX_PARAMS + 1];
     if (!fast)
         for (int p = 0; p <= P; ++p) acc[p] = 0.0;
 
@@ -312,8 +312,13 @@ int launch_grad_reduce(gpb_handle* h, const DevKernel& kp, const double* d_X, in
     double* partial = workspace(h, BUF_RED, (size_t)nblk * (GPB_MAX_PARAMS + 1) * sizeof(double));
     if (!partial) return -1;
     ProfScope prof(h, PROF_GRAD, h->stream);
-    GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv, ldk,
-                                                                                              d_alpha, partial)));
+    if (kp.n_leaves <= GRAD_FAST_LEAVES && !kp.has_ard) {
+        GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP, true><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv,
+                                                                                                        ldk, d_alpha, partial)));
+    } else {
+        GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP, false><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv,
+                                                                                                         ldk, d_alpha, partial)));
+    }
     int rc = check_cuda(h, cudaGetLastError(), "grad_reduce_kernel launch");
     if (rc) return rc;
     reduce_partials_kernel<<<kp.n_params + 1, 256, 0, h->stream>>>(partial, nblk, GPB_MAX_PARAMS + 1, d_out);
