@@ -9,9 +9,17 @@
 // tile is written once with 16-byte stores.
 //
 // HBM roofline: algorithmic bytes = 8*N*N2 (full) or 8*N(N+1)/2 (lower) written + 8*D*(N+N2) read.
+#include <stdlib.h>
+
 #include "engine.cuh"
 
 namespace gpb {
+
+static inline int pad_dims(int D) {
+    int dp = 1;
+    while (dp < D) dp <<= 1;
+    return dp;
+}
 
 constexpr int TILE = 64;       // output tile edge
 constexpr int ROWS_PT = 8;     // rows per thread
@@ -121,6 +129,243 @@ assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__
                 const int64_t gj = row0 + c0;
                 double v0 = stage[c0 * TILE + ((r + c0) & (TILE - 1))];
                 double v1 = stage[(c0 + 1) * TILE + ((r + c0 + 1) & (TILE - 1))];
+                double* p = Kout + gi * ldk + gj;
+                if (vec_ok && gj + 1 < N) {
+                    *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+                } else {
+                    if (gj < N) p[0] = v0;
+                    if (gj + 1 < N) p[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+// ---- Gram-form assembly on the FP64 tensor pipe ---------------------------------------------------------
+// For expressions whose groups are all EUCLID / DOT (no Periodic) with at most GRAM_GROUPS distance
+// groups: the per-group inner products x.x' of a 64 x 64 tile are 8x8x4 DMMA tiles over the (sqrt(w)-
+// scaled) coordinates, r^2 = |x|^2 + |x'|^2 - 2 x.x' costs three FP64 operations per element instead
+// of 3 D, and the leaves are evaluated four elements at a time (exp_vec).  This is what makes the
+// assembly approach the HBM roofline; the Gram form is also what GPflow evaluates.
+// Accuracy guard: an element falls back to the direct difference form when the
+// cancellation would be visible -- |x|^2 + |x'|^2 > 64 (non-standardised inputs), or, for the
+// non-smooth Matern12 / Exponential leaves, r^2 < 1e-8 (|x|^2 + |x'|^2) (near-coincident points).
+constexpr int GRAM_GROUPS = 2;
+
+template <int DP>
+struct GramSmem {
+    static constexpr int DPP = (DP % 8 == 0) ? DP + 4 : DP;   // row stride: conflict-free fragment loads
+    static constexpr int A = 0;                                // [G][64][DPP] scaled rows
+    static constexpr int B = A + GRAM_GROUPS * TILE * DPP;      // [G][64][DPP] scaled cols
+    static constexpr int NA = B + GRAM_GROUPS * TILE * DPP;     // [G][64]
+    static constexpr int NB_ = NA + GRAM_GROUPS * TILE;         // [G][64]
+    static constexpr int STAGE = NB_ + GRAM_GROUPS * TILE;      // [64][64] mirror staging
+    static constexpr int TOTAL = STAGE + TILE * TILE;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(ASM_THREADS, 2)
+assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
+                     const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
+                     double diag_add, int tiles_n, int has_kink) {
+    using L = GramSmem<DP>;
+    constexpr int DPP = L::DPP;
+    extern __shared__ __align__(16) double gsm[];
+    double* As = gsm + L::A;
+    double* Bs = gsm + L::B;
+    double* na = gsm + L::NA;
+    double* nb = gsm + L::NB_;
+    double* stage = gsm + L::STAGE;
+
+    int ti, tj;
+    if (mode == 0) {
+        ti = blockIdx.x / tiles_n;
+        tj = blockIdx.x % tiles_n;
+    } else {
+        tri_tile_index(blockIdx.x, ti, tj);
+    }
+    const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int G = kp.n_groups;
+
+    // stage sqrt(w)-scaled coordinates of both tile sides for every group
+    for (int e = tid; e < GRAM_GROUPS * TILE * DP; e += ASM_THREADS) {
+        const int gg = e / (TILE * DP), rem = e - gg * TILE * DP, r = rem / DP, d = rem - r * DP;
+        double a = 0.0, b = 0.0;
+        if (gg < G) {
+            const double sw = sqrt(kp.groups[gg].w[d]);
+            const int64_t gi = row0 + r, gj = col0 + r;
+            if (gi < N && d < D) a = sw * X[gi * D + d];
+            if (gj < N2 && d < D) b = sw * X2[gj * D + d];
+        }
+        As[(gg * TILE + r) * DPP + d] = a;
+        Bs[(gg * TILE + r) * DPP + d] = b;
+    }
+    __syncthreads();
+    for (int e = tid; e < GRAM_GROUPS * TILE; e += ASM_THREADS) {
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            const double a = As[e * DPP + d], b = Bs[e * DPP + d];
+            sa = fma(a, a, sa);
+            sb = fma(b, b, sb);
+        }
+        na[e] = sa;
+        nb[e] = sb;
+    }
+    __syncthreads();
+
+    const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(Kout) & 15) == 0);
+    const bool diag_tile = (mode != 0) && (ti == tj);
+    const int r = warp * 8 + g;               // tile row of this thread
+    // A fragments of this warp's 8 rows, all groups, all k-steps (reused for the 8 column tiles)
+    double afr[GRAM_GROUPS][DP / 4];
+#pragma unroll
+    for (int gg = 0; gg < GRAM_GROUPS; ++gg)
+#pragma unroll
+        for (int ks = 0; ks < DP / 4; ++ks) afr[gg][ks] = As[(gg * TILE + r) * DPP + ks * 4 + q];
+
+    // expression shape (uniform): a plain sum of leaves needs no products / selects
+    bool pure_sum = true;
+    double mult[GRAD_FAST_LEAVES] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < kp.n_terms; ++t) {
+        if (kp.terms[t].n_factors != 1) pure_sum = false;
+        const int id = kp.terms[t].leaf[0];
+#pragma unroll
+        for (int l = 0; l < GRAD_FAST_LEAVES; ++l) mult[l] += (id == l) ? 1.0 : 0.0;
+    }
+    double* const out_row = Kout + (row0 + r) * ldk + col0;
+
+#pragma unroll
+    for (int ct = 0; ct < TILE / 8; ct += 2) {
+        // four elements of this thread: (r, c), (r, c + 1), (r, c + 8), (r, c + 9) with c = ct*8 + 2q
+        const int c = ct * 8 + 2 * q;
+        double s[GRAM_GROUPS][4];
+#pragma unroll
+        for (int gg = 0; gg < GRAM_GROUPS; ++gg) {
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            if (gg < G) {
+#pragma unroll
+                for (int ks = 0; ks < DP / 4; ++ks) {
+                    const double b0 = Bs[(gg * TILE + ct * 8 + g) * DPP + ks * 4 + q];
+                    const double b1 = Bs[(gg * TILE + ct * 8 + 8 + g) * DPP + ks * 4 + q];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(d0), "+d"(d1) : "d"(afr[gg][ks]), "d"(b0));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(d2), "+d"(d3) : "d"(afr[gg][ks]), "d"(b1));
+                }
+            }
+            const double dots[4] = {d0, d1, d2, d3};
+            const bool euclid = (gg < G) && (kp.groups[gg].kind == GPB_GROUP_EUCLID);
+            const double nar = na[gg * TILE + r];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cc = c + (e & 1) + ((e >> 1) << 3);
+                double val = dots[e];
+                if (euclid) {
+                    const double nn = nar + nb[gg * TILE + cc];
+                    val = fma(-2.0, dots[e], nn);
+                    // integer tests on the high words (FP64 compares run on the slow XU pipe):
+                    //   val < 0 -> 0 ; nn > 64 ; val < 2^-27 nn (~7.5e-9 nn)
+                    const int hv = __double2hiint(val), hn = __double2hiint(nn);
+                    if (hv < 0) val = 0.0;
+                    if (hn > 0x40500000 || (has_kink && hv < hn - (27 << 20))) {   // cancellation guard: direct differences
+                        double acc2 = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) {
+                            const double t = As[(gg * TILE + r) * DPP + d] - Bs[(gg * TILE + cc) * DPP + d];
+                            acc2 = fma(t, t, acc2);
+                        }
+                        val = acc2;
+                    }
+                }
+                s[gg][e] = val;
+            }
+        }
+        // leaves, four elements at a time
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (pure_sum) {
+            // K = sum_l mult_l * leaf_l : accumulate straight into the outputs, no per-leaf arrays, no selects
+#pragma unroll
+            for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+                if (l < kp.n_leaves) {
+                    const DevLeaf& lf = kp.leaves[l];
+                    double vl[4];
+                    if (lf.group == 0) leaf_value_vec<4>(lf, s[0], vl);
+                    else leaf_value_vec<4>(lf, s[1], vl);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) out[e] = fma(mult[l], vl[e], out[e]);
+                }
+            }
+        } else {
+            double v[GRAD_FAST_LEAVES][4];
+#pragma unroll
+            for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[l][e] = 0.0;
+                if (l < kp.n_leaves) {
+                    const DevLeaf& lf = kp.leaves[l];
+                    if (lf.group == 0) leaf_value_vec<4>(lf, s[0], v[l]);
+                    else leaf_value_vec<4>(lf, s[1], v[l]);
+                }
+            }
+            for (int t = 0; t < kp.n_terms; ++t) {
+                const DevTerm& tm = kp.terms[t];
+                double prod[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+                for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
+                    if (f < tm.n_factors) {
+                        const int id = tm.leaf[f];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            double fv = v[0][e];
+#pragma unroll
+                            for (int l = 1; l < GRAD_FAST_LEAVES; ++l) fv = (id == l) ? v[l][e] : fv;
+                            prod[e] *= fv;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) out[e] += prod[e];
+            }
+        }
+        const int64_t gi = row0 + r;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int cc = c + 8 * h2;
+            double v0 = out[2 * h2], v1 = out[2 * h2 + 1];
+            if (diag_tile) {
+                if (r == cc) v0 += diag_add;
+                if (r == cc + 1) v1 += diag_add;
+            }
+            if (mode == 2) {
+                stage[r * TILE + ((cc + r) & (TILE - 1))] = v0;
+                stage[r * TILE + ((cc + 1 + r) & (TILE - 1))] = v1;
+            }
+            if (gi < N) {
+                const int64_t gj = col0 + cc;
+                double* p = out_row + cc;
+                if (vec_ok && gj + 1 < N2) {
+                    *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+                } else {
+                    if (gj < N2) p[0] = v0;
+                    if (gj + 1 < N2) p[1] = v1;
+                }
+            }
+        }
+    }
+    if (mode == 2 && ti != tj) {
+        __syncthreads();
+        const int tx = tid & 31, ty = tid >> 5, c0 = 2 * tx;
+#pragma unroll 1
+        for (int rr = 0; rr < ROWS_PT; ++rr) {
+            const int rw = ty * ROWS_PT + rr;
+            const int64_t gi = col0 + rw;
+            if (gi < N) {
+                const int64_t gj = row0 + c0;
+                const double v0 = stage[c0 * TILE + ((rw + c0) & (TILE - 1))];
+                const double v1 = stage[(c0 + 1) * TILE + ((rw + c0 + 1) & (TILE - 1))];
                 double* p = Kout + gi * ldk + gj;
                 if (vec_ok && gj + 1 < N) {
                     *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
@@ -266,12 +511,6 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int64
     if (threadIdx.x == 0) out[p] = sm[0];
 }
 
-static inline int pad_dims(int D) {
-    int dp = 1;
-    while (dp < D) dp <<= 1;
-    return dp;
-}
-
 #define GPB_DISPATCH_DP(D, CALL)                                   \
     switch (pad_dims(D)) {                                         \
         case 1: { constexpr int DP = 1; CALL; } break;             \
@@ -290,6 +529,45 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
     const int64_t nblk = (mode == 0) ? (int64_t)tiles_m * tiles_n : (int64_t)tiles_m * (tiles_m + 1) / 2;
     if (nblk > 0x7fffffffLL) return set_error(h, -2, "assemble: too many tiles");
     ProfScope prof(h, PROF_ASSEMBLE, h->stream);
+    // Gram-form / DMMA path: all groups EUCLID or DOT, at most two of them, at most four leaves, D >= 3
+    bool gram = (kp.n_groups <= GRAM_GROUPS) && (kp.n_leaves <= GRAD_FAST_LEAVES) && D >= 3 && !getenv("GPB_NO_GRAM");
+    int has_kink = 0;
+    for (int g = 0; g < kp.n_groups; ++g)
+        if (kp.groups[g].kind != GPB_GROUP_EUCLID && kp.groups[g].kind != GPB_GROUP_DOT) gram = false;
+    for (int l = 0; l < kp.n_leaves; ++l)
+        if (kp.leaves[l].kind == GPB_LEAF_MATERN12 || kp.leaves[l].kind == GPB_LEAF_EXPONENTIAL) has_kink = 1;
+    if (gram) {
+        cudaError_t e = cudaSuccess;
+        switch (pad_dims(D)) {
+            case 4: {
+                static bool set4 = false;
+                constexpr int SM = GramSmem<4>::TOTAL * (int)sizeof(double);
+                if (!set4) { e = cudaFuncSetAttribute(assemble_gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set4 = true; }
+                if (e == cudaSuccess)
+                    assemble_gram_kernel<4><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
+                                                                                          diag_add, tiles_n, has_kink);
+            } break;
+            case 8: {
+                static bool set8 = false;
+                constexpr int SM = GramSmem<8>::TOTAL * (int)sizeof(double);
+                if (!set8) { e = cudaFuncSetAttribute(assemble_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set8 = true; }
+                if (e == cudaSuccess)
+                    assemble_gram_kernel<8><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
+                                                                                          diag_add, tiles_n, has_kink);
+            } break;
+            default: {
+                static bool set16 = false;
+                constexpr int SM = GramSmem<16>::TOTAL * (int)sizeof(double);
+                if (!set16) { e = cudaFuncSetAttribute(assemble_gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set16 = true; }
+                if (e == cudaSuccess)
+                    assemble_gram_kernel<16><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
+                                                                                           diag_add, tiles_n, has_kink);
+            } break;
+        }
+        if (e != cudaSuccess) return check_cuda(h, e, "assemble_gram cudaFuncSetAttribute");
+        h->launches += 1;
+        return check_cuda(h, cudaGetLastError(), "assemble_gram_kernel launch");
+    }
     GPB_DISPATCH_DP(D, (assemble_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(
                            kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n)));
     h->launches += 1;

@@ -34,6 +34,10 @@ static __constant__ double GPB_EXPC[14] = {1.0, 1.0, 0.5, 1.6666666666666666e-01
 static __constant__ double GPB_EXPK[4] = {1.4426950408889634, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
                                    6755399441055744.0};
 
+// FP64 compares / min / max (DSETP, DMNMX) issue on the low-rate XU pipe on sm_100 (ncu: xu 88 % busy with
+// them in the element loops), so range checks here are INTEGER tests on the high word of the double.
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
 template <int V>
 __device__ __forceinline__ void exp_vec(double (&x)[V]) {
     double r[V], p[V];
@@ -41,9 +45,9 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
     const double l2e = GPB_EXPK[0], ln2h = GPB_EXPK[1], ln2l = GPB_EXPK[2], magic = GPB_EXPK[3];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        // the rint-by-magic-constant trick needs |x log2 e| < 2^31: clamp to the range where exp is finite
-        // and non-zero (trial points of the line search can make r^2 / l^2 astronomically large)
-        const double xc = fmin(fmax(x[v], -760.0), 709.0);
+        // |x| >= 704 (incl. inf / NaN): out of the fast range, fixed up below; evaluate a harmless argument
+        const bool big = hi_abs(x[v]) >= 0x40860000;
+        const double xc = big ? 0.0 : x[v];
         const double t = fma(xc, l2e, magic);
         k[v] = __double2loint(t);
         const double n = t - magic;
@@ -58,10 +62,9 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const int k1 = max(k[v], -1000);
-        double res = p[v] * __hiloint2double((k1 + 1023) << 20, 0);
-        if (k[v] != k1) res = (x[v] < -750.0) ? 0.0 : res * __hiloint2double((max(k[v] - k1, -200) + 1023) << 20, 0);
-        x[v] = (x[v] != x[v]) ? x[v] : res;   // NaN in, NaN out
+        double res = p[v] * __hiloint2double((k[v] + 1023) << 20, 0);   // |k| <= 1016: always a normal scale
+        if (hi_abs(x[v]) >= 0x40860000) res = exp(x[v]);                // rare: underflow window, 0, inf, NaN
+        x[v] = res;
     }
 }
 
@@ -462,7 +465,8 @@ __device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const double u = s[e] * lf.scale;
-                r[e] = lf.arg_is_r ? u : sqrt(fmax(u, 1e-36));
+                // sqrt(max(u, 1e-36)) with an integer test on the high word (u >= 0 here): hi(1e-36) = 0x38754484
+                r[e] = lf.arg_is_r ? u : ((__double2hiint(u) < 0x38754484) ? 1e-18 : sqrt(u));
                 a[e] = -c * r[e];
             }
             exp_vec<V>(a);
