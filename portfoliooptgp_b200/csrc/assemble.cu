@@ -259,28 +259,40 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
             const double dots[4] = {d0, d1, d2, d3};
             const bool euclid = (gg < G) && (kp.groups[gg].kind == GPB_GROUP_EUCLID);
             const double nar = na[gg * TILE + r];
+            if (euclid) {
+                // r^2 = |x|^2 + |x'|^2 - 2 x.x' ; integer tests on the high words (FP64 compares are slow):
+                //   negative -> 0 ; cancellation guard |x|^2+|x'|^2 > 64, or (kink kernels) r^2 < 2^-27 (...)
+                int guard = 0;
+                double nn[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int cc = c + (e & 1) + ((e >> 1) << 3);
-                double val = dots[e];
-                if (euclid) {
-                    const double nn = nar + nb[gg * TILE + cc];
-                    val = fma(-2.0, dots[e], nn);
-                    // integer tests on the high words (FP64 compares run on the slow XU pipe):
-                    //   val < 0 -> 0 ; nn > 64 ; val < 2^-27 nn (~7.5e-9 nn)
-                    const int hv = __double2hiint(val), hn = __double2hiint(nn);
+                for (int e = 0; e < 4; ++e) {
+                    const int cc = c + (e & 1) + ((e >> 1) << 3);
+                    nn[e] = nar + nb[gg * TILE + cc];
+                    double val = fma(-2.0, dots[e], nn[e]);
+                    const int hv = __double2hiint(val), hn = __double2hiint(nn[e]);
                     if (hv < 0) val = 0.0;
-                    if (hn > 0x40500000 || (has_kink && hv < hn - (27 << 20))) {   // cancellation guard: direct differences
-                        double acc2 = 0.0;
+                    guard |= (hn > 0x40500000) | (has_kink & (hv < hn - (27 << 20)));
+                    s[gg][e] = val;
+                }
+                if (guard) {   // one (rare) branch for the four elements: direct differences where needed
 #pragma unroll
-                        for (int d = 0; d < DP; ++d) {
-                            const double t = As[(gg * TILE + r) * DPP + d] - Bs[(gg * TILE + cc) * DPP + d];
-                            acc2 = fma(t, t, acc2);
+                    for (int e = 0; e < 4; ++e) {
+                        const int cc = c + (e & 1) + ((e >> 1) << 3);
+                        const int hv = __double2hiint(s[gg][e]), hn = __double2hiint(nn[e]);
+                        if (hn > 0x40500000 || (has_kink && hv < hn - (27 << 20))) {
+                            double acc2 = 0.0;
+#pragma unroll
+                            for (int d = 0; d < DP; ++d) {
+                                const double t = As[(gg * TILE + r) * DPP + d] - Bs[(gg * TILE + cc) * DPP + d];
+                                acc2 = fma(t, t, acc2);
+                            }
+                            s[gg][e] = acc2;
                         }
-                        val = acc2;
                     }
                 }
-                s[gg][e] = val;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[gg][e] = dots[e];
             }
         }
         // leaves, four elements at a time

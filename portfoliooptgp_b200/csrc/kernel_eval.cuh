@@ -60,11 +60,18 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
 #pragma unroll
         for (int v = 0; v < V; ++v) p[v] = fma(p[v], r[v], c);
     }
+    int worst = 0;   // one branch for the whole vector instead of one per element
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        double res = p[v] * __hiloint2double((k[v] + 1023) << 20, 0);   // |k| <= 1016: always a normal scale
-        if (hi_abs(x[v]) >= 0x40860000) res = exp(x[v]);                // rare: underflow window, 0, inf, NaN
-        x[v] = res;
+    for (int v = 0; v < V; ++v) worst = max(worst, hi_abs(x[v]));
+    if (worst >= 0x40860000) {                                          // rare: underflow window, 0, inf, NaN
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const double res = p[v] * __hiloint2double((k[v] + 1023) << 20, 0);
+            x[v] = (hi_abs(x[v]) >= 0x40860000) ? exp(x[v]) : res;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) x[v] = p[v] * __hiloint2double((k[v] + 1023) << 20, 0);   // |k| <= 1016: normal scale
     }
 }
 
