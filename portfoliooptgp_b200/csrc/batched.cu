@@ -18,7 +18,7 @@
 
 namespace gpb {
 
-constexpr int BT = 256;  // threads per CTA
+constexpr int BT = 512;  // threads per CTA (16 warps: four per scheduler to hide the FP64 / DMMA / shared-memory latencies)
 constexpr int BW = BT / 32;
 
 struct BatchedSmem {
@@ -36,7 +36,7 @@ template <int DP>
 constexpr size_t batched_smem_bytes() { return (size_t)(BatchedSmem::XS + 128 * (DP + 1) + 16) * sizeof(double); }
 
 // mode 0: LML only; 1: LML + gradient; 2: predict_f at Ns points per GP
-template <int DP>
+template <int DP, bool FAST>
 __global__ void __launch_bounds__(BT, 1)
 batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kbad, const double* __restrict__ X,
                   const double* __restrict__ Yc, const double* __restrict__ noise,
@@ -195,11 +195,11 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
     double* o = out + (size_t)b * (2 + P);
     if (mode == 1) {
         // ---- gradient: K^-1 tile = sum_{k >= ti*8} W[k, ti-blk]^T W[k, tj-blk] on DMMA, consumed in place
-        const bool fast = grad_fast_ok(kp);
+        constexpr bool fast = FAST;   // register accumulators (<= 4 leaves, no ARD) vs generic path: two kernels
         GradAcc A;
         A.zero();
         double tr = 0.0;
-        double acc[GPB_MAX_PARAMS + 1];
+        double acc[FAST ? 1 : GPB_MAX_PARAMS + 1];
         if (!fast)
             for (int p = 0; p <= P; ++p) acc[p] = 0.0;
         for (int t = warp; t < nt8 * (nt8 + 1) / 2; t += BW) {
@@ -270,11 +270,11 @@ __global__ void build_dev_kernels_kernel(const __grid_constant__ gpb_kernel_spec
     bad[b] = build_dev_kernel_core(spec, theta + b * spec.n_params, out + b);
 }
 
-template <int DP>
+template <int DP, bool FAST>
 static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
                              const double* d_noise, int64_t B, int N, int D, int mode, double* d_out, int* d_info,
                              const double* d_Xs, int Ns, double* d_mean, double* d_var) {
-    auto kern = batched_gp_kernel<DP>;
+    auto kern = batched_gp_kernel<DP, FAST>;
     constexpr size_t SMEM = batched_smem_bytes<DP>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -322,12 +322,20 @@ int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const d
     if (B > 0x7fffffffLL) return set_error(h, -2, "batched: B too large");
     int dp = 1;
     while (dp < D) dp <<= 1;
+    bool fast = (h->spec.n_leaves <= GRAD_FAST_LEAVES);
+    for (int g = 0; g < h->spec.n_groups; ++g)
+        if (h->spec.groups[g].ard_index >= 0) fast = false;
     switch (dp) {
-        case 1: return launch_batched_dp<1>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var);
-        case 2: return launch_batched_dp<2>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var);
-        case 4: return launch_batched_dp<4>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var);
-        case 8: return launch_batched_dp<8>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var);
-        default: return launch_batched_dp<16>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var);
+        case 1: return (fast ? launch_batched_dp<1, true>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var)
+                          : launch_batched_dp<1, false>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var));
+        case 2: return (fast ? launch_batched_dp<2, true>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var)
+                          : launch_batched_dp<2, false>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var));
+        case 4: return (fast ? launch_batched_dp<4, true>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var)
+                          : launch_batched_dp<4, false>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var));
+        case 8: return (fast ? launch_batched_dp<8, true>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var)
+                          : launch_batched_dp<8, false>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var));
+        default: return (fast ? launch_batched_dp<16, true>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var)
+                          : launch_batched_dp<16, false>(h, d_X, d_Yc, d_theta, d_noise, B, (int)N, D, mode, d_out, d_info, d_Xs, (int)Ns, d_mean, d_var));
     }
 }
 
