@@ -100,7 +100,8 @@ int gpb_version(void);
 int64_t gpb_launch_count(gpb_handle* h);
 
 /* Engine options.  option 0: fork off-critical-path products of the blocked factorisation onto side
- * streams (default 1; bench.py switches it off while it times individual kernels). */
+ * streams (default 1; bench.py switches it off while it times individual kernels).  option 1: launch
+ * the GEMM / leaf kernels with programmatic dependent launch (default 1). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 
 /* Optional kernel timing with CUDA events recorded on the handle's stream around each engine

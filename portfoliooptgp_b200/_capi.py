@@ -164,6 +164,7 @@ class Engine:
     PROF_CATEGORIES = ("gemm", "assemble", "leaf", "grad_reduce", "vector", "batched", "svgp", "other")
 
     OPTION_FORK_STREAMS = 0
+    OPTION_PDL = 1
 
     def set_option(self, option: int, value: int):
         self._check(self._lib.gpb_set_option(self._h, int(option), int(value)), "gpb_set_option")

@@ -216,6 +216,7 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
     if (!h) return -1;
     switch (option) {
         case 0: h->fork_streams = (value != 0); return 0;
+        case 1: h->use_pdl = (value != 0); return 0;
         default: return set_error(h, -2, "unknown option %d", option);
     }
 }

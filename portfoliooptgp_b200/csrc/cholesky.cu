@@ -34,6 +34,8 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     double* T = sm + NB * SLD;
     double* dinv = T + 64 * TLD;
     int* fail = reinterpret_cast<int*>(dinv + DINV_DOUBLES);
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int np = (n + 7) & ~7;
     // 128 x 128 block, 512 threads: 32 elements per thread, all loads in flight before the stores
@@ -90,9 +92,16 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
         attr_set = true;
     }
     ProfScope prof(h, PROF_LEAF, h->stream);
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A + (int64_t)offset * lda + offset, lda,
-                                                                     W + (int64_t)offset * ldw + offset, ldw, n, offset,
-                                                                     logdiag, info, store_L ? 1 : 0);
+    if (h->use_pdl) {
+        cudaError_t le = launch_pdl(leaf_potrf_inv_kernel, dim3(1), dim3(LEAF_THREADS), LEAF_SMEM, h->stream,
+                                    A + (int64_t)offset * lda + offset, lda, W + (int64_t)offset * ldw + offset, ldw, n,
+                                    offset, logdiag, info, store_L ? 1 : 0);
+        if (le != cudaSuccess) return check_cuda(h, le, "leaf launch (PDL)");
+    } else {
+        leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A + (int64_t)offset * lda + offset, lda,
+                                                                         W + (int64_t)offset * ldw + offset, ldw, n, offset,
+                                                                         logdiag, info, store_L ? 1 : 0);
+    }
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "leaf_potrf_inv_kernel launch");
 }

@@ -144,6 +144,8 @@ dgemm_kernel(const GemmParams p) {
     kbeg = (kbeg / BK) * BK;
     const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
 
+    pdl_launch_dependents();   // the next kernel in the stream may start its prologue
+    pdl_wait();                // ... and this one waits here for its predecessor's results
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
     const int g = lane >> 2, q = lane & 3;
@@ -240,7 +242,11 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     int64_t grid = p.tri ? (int64_t)(BM / BN) * tm * (tm + 1) / 2 : (int64_t)tm * tn;
     if (grid <= 0) return 0;
     ProfScope prof(h, PROF_GEMM, stream);
-    kern<<<(unsigned)grid, NT, SMEM, stream>>>(p);
+    {
+        cudaError_t le = h->use_pdl ? launch_pdl(kern, dim3((unsigned)grid), dim3(NT), SMEM, stream, p)
+                                    : (kern<<<(unsigned)grid, NT, SMEM, stream>>>(p), cudaSuccess);
+        if (le != cudaSuccess) return check_cuda(h, le, "dgemm_kernel launch (PDL)");
+    }
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "dgemm_kernel launch");
 }

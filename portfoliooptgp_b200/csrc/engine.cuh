@@ -19,6 +19,7 @@ struct gpb_handle {
     cudaEvent_t ev_fork[MAX_DEPTH] = {}, ev_join[MAX_DEPTH] = {};
     std::string err;
     bool fork_streams = true;   // gpb_set_option(h, 0, x)
+    bool use_pdl = true;        // gpb_set_option(h, 1, x): programmatic dependent launch for dgemm / leaf
     int64_t launches = 0;
     int sm_count = 148;
 
@@ -46,6 +47,28 @@ struct gpb_handle {
 };
 
 namespace gpb {
+
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may begin (block scheduling,
+// prologue) while its predecessor in the stream is still draining; it must call pdl_wait() before it
+// touches global memory, and the predecessor calls pdl_launch_dependents() early to allow it.  Used for
+// the ~300 short dependent launches at the bottom of the blocked factorisation.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7 };
 
