@@ -1,6 +1,7 @@
 """Prediction post-processing of the reference's Predictor (GPR/predictor.py:10-51):
 linear-interpolation upsampling of the weekly / monthly predictions onto the daily grid and the
-alpha / beta blend of the three time frames.  O(N*) host arithmetic on the [N*,1] outputs of
+alpha / beta blend of the three time frames, plus the SLSQP solve for the blend weights
+(GPR/optimizer.py:5-28).  O(N*) host arithmetic on the [N*,1] outputs of
 predict_f / predict_y; kept out of the device path on purpose (a few hundred values)."""
 from __future__ import annotations
 
@@ -65,3 +66,29 @@ class Predictor:
 
     def upsample_predictions(self, X_daily, X, predictions, period="d"):
         return upsample_predictions(X_daily, X, predictions, period)
+
+
+class Optimizer:
+    """Blend-weight solve of GPR/optimizer.py:5-28: minimise  MSE(Y, a*daily + b*weekly + (1-a-b)*monthly)
+    + lambda (|a| + |b|)  over 0 <= a, b <= 1, a + b <= 1 with SciPy's SLSQP from (0.33, 0.33).  A
+    two-variable host problem on predictions that are already on the host; same attribute and
+    method names as the reference class."""
+
+    def __init__(self, lambda_=0.01):
+        self.lambda_ = lambda_
+        self.initial_weights = [0.33, 0.33]
+        self.bounds = [(0, 1), (0, 1)]
+        self.constraints = {"type": "ineq", "fun": lambda w: 1 - sum(w)}
+
+    def loss_fn(self, weights, Y, f_mean_daily, f_mean_weekly, f_mean_monthly):
+        a, b = weights
+        resid = _np(Y) - (a * _np(f_mean_daily) + b * _np(f_mean_weekly) + (1 - a - b) * _np(f_mean_monthly))
+        # sklearn's mean_squared_error on [N,1] columns: mean over rows, uniform average over outputs
+        return float(np.mean(resid * resid)) + self.lambda_ * (abs(a) + abs(b))
+
+    def optimize_weights(self, Y_tf, f_mean_daily, f_mean_weekly, f_mean_monthly):
+        from scipy.optimize import minimize
+
+        res = minimize(lambda w: self.loss_fn(w, Y_tf, f_mean_daily, f_mean_weekly, f_mean_monthly),
+                       self.initial_weights, bounds=self.bounds, constraints=self.constraints, method="SLSQP")
+        return res.x

@@ -28,3 +28,29 @@ def test_predict_combined_blend():
     m = tuple(np.full((2, 1), v) for v in (100.0, 200.0, 300.0, 400.0))
     out = predict_combined(0.5, 0.3, d, w, m, xd, xw, xm)
     assert np.allclose(out[0], 0.5 * 1 + 0.3 * 10 + 0.2 * 100) and np.allclose(out[3], 0.5 * 4 + 0.3 * 40 + 0.2 * 400)
+
+
+def test_blend_weight_optimizer_matches_reference_formulation():
+    """GPR/optimizer.py:13-28 restated with sklearn + SLSQP here; same optimum and same loss."""
+    from scipy.optimize import minimize
+    from sklearn.metrics import mean_squared_error
+
+    from portfoliooptgp_b200.postprocess import Optimizer
+
+    rng = np.random.default_rng(11)
+    n = 200
+    d, w, m = (rng.normal(size=(n, 1)) for _ in range(3))
+    Y = 0.55 * d + 0.3 * w + 0.15 * m + 0.01 * rng.normal(size=(n, 1))
+    opt = Optimizer(lambda_=0.01)
+    got = opt.optimize_weights(Y, d, w, m)
+
+    def ref_loss(x):
+        a, b = x
+        return mean_squared_error(Y, a * d + b * w + (1 - a - b) * m) + 0.01 * (np.abs(a) + np.abs(b))
+
+    ref = minimize(ref_loss, [0.33, 0.33], bounds=[(0, 1), (0, 1)],
+                   constraints={"type": "ineq", "fun": lambda x: 1 - sum(x)}, method="SLSQP").x
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+    assert abs(opt.loss_fn(got, Y, d, w, m) - ref_loss(ref)) < 1e-12
+    assert 0 <= got[0] <= 1 and 0 <= got[1] <= 1 and got.sum() <= 1 + 1e-9
+    assert abs(got[0] - 0.55) < 0.05 and abs(got[1] - 0.3) < 0.05
