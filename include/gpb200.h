@@ -213,6 +213,29 @@ int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, 
 int gpb_adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double* d_v, int64_t n,
                   double lr, double beta1, double beta2, double eps, int64_t step, int maximize);
 
+/* ---- device-side data preparation (the step before the path) ---------------
+ * Series are [T, A] row-major in device memory (T time steps, one column per asset / field).
+ * Replaces the pandas arithmetic of Multi-Input_GPR/utils/data_handler.py:86-91 (returns),
+ * :160-169 (normalize_and_reshape), :129-154 (concatenate_X) and the window slicing of
+ * Multi-Input_GPR/main.py:414-423 for data that is already resident in HBM.
+ *
+ * gpb_prep_returns: kind 0 = close.pct_change() with row 0 filled from row 1 (data_handler.py:86-88);
+ *   kind 1 = (close - open) / open (:89); kind 2 = log(close / close.shift(1)), +-inf -> 0, row 0 NaN
+ *   (:90-91).  d_open is read by kind 1 only. */
+int gpb_prep_returns(gpb_handle* h, const double* d_close, const double* d_open, int64_t T, int64_t A,
+                     int kind, double* d_out);
+/* Per-column mean and standard deviation (ddof = 1 is pandas' Series.std, ddof = 0 numpy's) and, if
+ * d_out is not NULL, d_out[t*ldo + a] = (x[t,a] - mean[a]) / std[a]: with ldo > A and an offset
+ * d_out pointer several z-scored blocks land side by side in one [T, D] design matrix
+ * (concatenate_X).  d_mean / d_std [A] may be NULL. */
+int gpb_prep_zscore(gpb_handle* h, const double* d_x, int64_t T, int64_t A, int ddof, double* d_out,
+                    int64_t ldo, double* d_mean, double* d_std);
+/* Window gather: d_feat [S, T, D], d_y [S, T] (or NULL)  ->  d_X [S*W, N, D], d_Y [S*W, N] with
+ * W = (T - N) / stride + 1 windows per series, window w covering rows w*stride .. w*stride+N-1:
+ * the [B, N, D] batch gpb_batched_lml_grad consumes.  T < N produces no window (returns 0). */
+int gpb_prep_windows(gpb_handle* h, const double* d_feat, const double* d_y, int64_t S, int64_t T, int D,
+                     int64_t N, int64_t stride, double* d_X, double* d_Y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,9 @@ SIGNATURES = {
     "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
     "gpb_svgp_predict_f": (_INT, [_P, _DP, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
     "gpb_adam_step": (_INT, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _I64, _INT]),
+    "gpb_prep_returns": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
+    "gpb_prep_zscore": (_INT, [_P, _P, _I64, _I64, _INT, _P, _I64, _P, _P]),
+    "gpb_prep_windows": (_INT, [_P, _P, _P, _I64, _I64, _INT, _I64, _I64, _P, _P]),
 }
 
 
@@ -273,6 +276,18 @@ class Engine:
                   eps=1e-8, maximize: bool = True):
         self._check(self._lib.gpb_adam_step(self._h, _P(dx), _P(dg), _P(dm), _P(dv), n, float(lr), float(beta1),
                                             float(beta2), float(eps), int(step), int(bool(maximize))), "gpb_adam_step")
+
+    def prep_returns(self, dclose: int, dopen: int, T: int, A: int, kind: int, dout: int):
+        self._check(self._lib.gpb_prep_returns(self._h, _P(dclose), _P(dopen), T, A, int(kind), _P(dout)),
+                    "gpb_prep_returns")
+
+    def prep_zscore(self, dx: int, T: int, A: int, ddof: int, dout: int, ldo: int, dmean: int, dstd: int):
+        self._check(self._lib.gpb_prep_zscore(self._h, _P(dx), T, A, int(ddof), _P(dout), ldo, _P(dmean), _P(dstd)),
+                    "gpb_prep_zscore")
+
+    def prep_windows(self, dfeat: int, dy: int, S: int, T: int, D: int, N: int, stride: int, dX: int, dY: int):
+        self._check(self._lib.gpb_prep_windows(self._h, _P(dfeat), _P(dy), S, T, D, N, stride, _P(dX), _P(dY)),
+                    "gpb_prep_windows")
 
     def gpr_get_alpha(self, dalpha: int):
         self._check(self._lib.gpb_gpr_get_alpha(self._h, _P(dalpha)), "gpb_gpr_get_alpha")
