@@ -207,6 +207,21 @@ int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, 
                        const double* d_qmu, const double* d_qsqrt, int64_t ldq, const double* d_Xs,
                        int64_t Ns, double* d_mean, double* d_var);
 
+/* ---- SGPR: Titsias' collapsed sparse bound (gpflow/models/sgpr.py SGPR.elbo / predict_f; the model
+ * built at test_scripts/SVGP.py:393-399 and trained with Scipy).  d_Z [M, D] inducing points, d_X [N, D],
+ * d_err [N] = Y - mean_function(X); jitter 1e-6 on Kuu as gpflow.config.default_jitter().
+ * h_out (host) [2 + n_params + M*D] = elbo, d elbo/d noise_variance, d elbo/d theta (constrained, engine
+ * order), d elbo/d Z (row-major); only h_out[0] is written when want_grad == 0.  d_errbar [N] (device,
+ * may be NULL) = d elbo/d err for mean-function parameters.  Returns > 0 = 1-based failing pivot of
+ * Kuu or of I + A A^T ("Cholesky decomposition was not successful"). */
+int gpb_sgpr_elbo(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z, int64_t M,
+                  int D, const double* d_X, const double* d_err, int64_t N, int want_grad, double* h_out,
+                  double* d_errbar);
+/* SGPR.predict_f(Xnew, full_cov=False): d_mean, d_var [Ns] (mean excludes mean_function(Xnew)). */
+int gpb_sgpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z,
+                       int64_t M, int D, const double* d_X, const double* d_err, int64_t N,
+                       const double* d_Xs, int64_t Ns, double* d_mean, double* d_var);
+
 /* Adam update of a device-resident parameter block in place (x += / -= lr * mhat / (sqrt(vhat) + eps));
  * used by the data-parallel minibatch SVGP loop for Z, q_mu, q_sqrt (identity transforms), where
  * GPflow users run tf.optimizers.Adam on minibatches.  step >= 1 is the 1-based iteration. */

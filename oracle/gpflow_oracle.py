@@ -507,3 +507,60 @@ def svgp_elbo(kernel, Z, q_mu, q_sqrt, noise_variance, X, Y, num_data=None, whit
                      - 0.5 * (np.square(Y - fmean) + fvar) / noise_variance, axis=-1)
     scale = 1.0 if num_data is None else float(num_data) / X.shape[0]
     return float(np.sum(var_exp) * scale - kl)
+
+
+# ---- SGPR: gpflow/models/sgpr.py (2.9.1) SGPR_deprecated._common_calculation / elbo / predict_f --------
+# reference call site: test_scripts/SVGP.py:393-399 (SGPR(data, SquaredExponential(), inducing_variable=Z)
+# trained by Scipy in plot_model, then predict_y)
+def _sgpr_common(kernel, Z, noise_variance, X):
+    Z = np.asarray(Z, dtype=np.float64)
+    M = Z.shape[0]
+    Kdiag = K_diag(kernel, X)
+    kuf = K(kernel, Z, X)
+    kuu = K(kernel, Z) + DEFAULT_JITTER * np.eye(M)
+    L = sla.cholesky(kuu, lower=True, check_finite=False)
+    sigma_sq = float(noise_variance)
+    sigma = np.sqrt(sigma_sq)
+    A = sla.solve_triangular(L, kuf, lower=True, check_finite=False) / sigma
+    AAT = A @ A.T
+    B = AAT + np.eye(M)
+    LB = sla.cholesky(B, lower=True, check_finite=False)
+    return Kdiag, L, sigma_sq, sigma, A, AAT, LB
+
+
+def sgpr_elbo(kernel, Z, noise_variance, X, Y, mean=None):
+    """SGPR.elbo = const + logdet_term + quad_term (one output column)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(len(X), -1)
+    N, outdim = Y.shape
+    Kdiag, L, sigma_sq, sigma, A, AAT, LB = _sgpr_common(kernel, Z, noise_variance, X)
+    # logdet_term
+    half_logdet_b = np.sum(np.log(np.diag(LB)))
+    log_sigma_sq = N * np.log(sigma_sq)
+    logdet_k = -outdim * (half_logdet_b + 0.5 * log_sigma_sq)
+    trace_k = np.sum(Kdiag / sigma_sq)
+    trace_q = np.trace(AAT)
+    logdet = logdet_k + 0.5 * outdim * (trace_q - trace_k)
+    # quad_term
+    err = Y - (0.0 if mean is None else np.asarray(mean, dtype=np.float64).reshape(N, -1))
+    Aerr = A @ (err / sigma)
+    c = sla.solve_triangular(LB, Aerr, lower=True, check_finite=False)
+    quad = -0.5 * (np.sum(np.square(err) / sigma_sq) - np.sum(np.square(c)))
+    const = -0.5 * N * outdim * np.log(2 * np.pi)
+    return float(const + logdet + quad)
+
+
+def sgpr_predict_f(kernel, Z, noise_variance, X, Y, Xnew, mean=None):
+    """SGPR.predict_f(Xnew, full_cov=False) without the mean function added back."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(len(X), -1)
+    Kdiag, L, sigma_sq, sigma, A, AAT, LB = _sgpr_common(kernel, Z, noise_variance, X)
+    err = Y - (0.0 if mean is None else np.asarray(mean, dtype=np.float64).reshape(len(X), -1))
+    Kus = K(kernel, np.asarray(Z, dtype=np.float64), Xnew)
+    Aerr = A @ err
+    c = sla.solve_triangular(LB, Aerr, lower=True, check_finite=False) / sigma
+    tmp1 = sla.solve_triangular(L, Kus, lower=True, check_finite=False)
+    tmp2 = sla.solve_triangular(LB, tmp1, lower=True, check_finite=False)
+    fmean = tmp2.T @ c
+    fvar = K_diag(kernel, Xnew) + np.sum(np.square(tmp2), 0) - np.sum(np.square(tmp1), 0)
+    return fmean, np.tile(fvar[:, None], (1, Y.shape[1]))

@@ -37,6 +37,18 @@ def square_distance(X, X2=None):  # gpflow/utilities/ops.py (G3)
     return -2.0 * (X @ X2.T) + Xs[:, None] + X2s[None, :]
 
 
+def direct_square_distance(X, X2=None):
+    """sum_d (x_d - x'_d)^2 evaluated directly (see gpflow_oracle.direct_square_distance)."""
+    X2 = X if X2 is None else X2
+    d = X[:, None, :] - X2[None, :, :]
+    return torch.sum(d * d, dim=-1)
+
+
+def _sqdist(X, X2):
+    # follows gpflow_oracle.set_distance_form so both oracles flip together
+    return square_distance(X, X2) if O._DISTANCE_FORM == "gram" else direct_square_distance(X, X2)
+
+
 def _k_r2(kind, variance, r2, alpha):
     if kind == "se":
         return variance * torch.exp(-0.5 * r2)
@@ -102,7 +114,7 @@ def K(kernel, th: _Theta, X, X2=None):
     if kernel.kind == "linear":
         return (Xs * th.get(kernel, "variance")) @ (Xs if X2s is None else X2s).T
     ls = th.get(kernel, "lengthscales")
-    r2 = square_distance(Xs / ls, None if X2s is None else X2s / ls)
+    r2 = _sqdist(Xs / ls, None if X2s is None else X2s / ls)
     alpha = th.get(kernel, "alpha") if kernel.kind == "rq" else None
     return _k_r2(kernel.kind, th.get(kernel, "variance"), r2, alpha)
 
@@ -192,3 +204,39 @@ def svgp_elbo_and_grad(kernel, Z, q_mu, q_sqrt, noise_variance, X, Y, num_data=N
     g = torch.autograd.grad(elbo, [theta, Zt, qm, qs, nv])
     return float(elbo.detach()), {"theta": g[0].numpy().copy(), "Z": g[1].numpy().copy(), "q_mu": g[2].numpy().copy(),
                          "q_sqrt": np.tril(g[3].numpy()).copy(), "noise": float(g[4])}
+
+
+def sgpr_elbo(kernel, theta, Z, noise_variance, X, err):
+    """SGPR.elbo (gpflow/models/sgpr.py), differentiable in theta, Z, noise_variance and err = Y - m(X)."""
+    th = _Theta(kernel, theta)
+    M, N = Z.shape[0], X.shape[0]
+    Kdiag = K_diag(kernel, th, X)
+    kuf = K(kernel, th, Z, X)
+    kuu = K(kernel, th, Z) + O.DEFAULT_JITTER * torch.eye(M, dtype=_D)
+    L = torch.linalg.cholesky(kuu)
+    sigma = torch.sqrt(noise_variance)
+    A = torch.linalg.solve_triangular(L, kuf, upper=False) / sigma
+    AAT = A @ A.T
+    LB = torch.linalg.cholesky(AAT + torch.eye(M, dtype=_D))
+    half_logdet_b = torch.sum(torch.log(torch.diagonal(LB)))
+    logdet = -(half_logdet_b + 0.5 * N * torch.log(noise_variance)) + 0.5 * (torch.trace(AAT) - torch.sum(Kdiag / noise_variance))
+    Aerr = A @ (err / sigma)
+    c = torch.linalg.solve_triangular(LB, Aerr, upper=False)
+    quad = -0.5 * (torch.sum(torch.square(err) / noise_variance) - torch.sum(torch.square(c)))
+    return -0.5 * N * math.log(2 * math.pi) + logdet + quad
+
+
+def sgpr_elbo_and_grad(kernel, Z, noise_variance, X, Y, mean=None):
+    """(elbo, gradients w.r.t. constrained theta, Z, noise variance and err) by reverse-mode autodiff."""
+    theta = torch.tensor(O.get_theta(kernel), dtype=_D, requires_grad=True)
+    Zt = torch.tensor(np.asarray(Z, dtype=np.float64), requires_grad=True)
+    nv = torch.tensor(float(noise_variance), dtype=_D, requires_grad=True)
+    Xt = torch.as_tensor(np.asarray(X, dtype=np.float64))
+    e = np.asarray(Y, dtype=np.float64).reshape(len(Y), 1)
+    if mean is not None:
+        e = e - np.asarray(mean, dtype=np.float64).reshape(len(Y), 1)
+    et = torch.tensor(e, requires_grad=True)
+    elbo = sgpr_elbo(kernel, theta, Zt, nv, Xt, et)
+    g = torch.autograd.grad(elbo, [theta, Zt, nv, et])
+    return float(elbo.detach()), {"theta": g[0].numpy().copy(), "Z": g[1].numpy().copy(), "noise": float(g[2]),
+                                  "err": g[3].numpy()[:, 0].copy()}

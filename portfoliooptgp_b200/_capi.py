@@ -92,6 +92,8 @@ SIGNATURES = {
     "gpb_svgp_data_term": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _P, _I64, _P, _INT]),
     "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
     "gpb_svgp_predict_f": (_INT, [_P, _DP, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
+    "gpb_sgpr_elbo": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _INT, _DP, _P]),
+    "gpb_sgpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
     "gpb_adam_step": (_INT, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _I64, _INT]),
     "gpb_prep_returns": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
     "gpb_prep_zscore": (_INT, [_P, _P, _I64, _I64, _INT, _P, _I64, _P, _P]),
@@ -271,6 +273,19 @@ class Engine:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         self._check(self._lib.gpb_svgp_predict_f(self._h, _as_dp(theta), _P(dZ), M, D, _P(dqmu), _P(dqsqrt), ldq, _P(dXs),
                                                  Ns, _P(dmean), _P(dvar)), "gpb_svgp_predict_f")
+
+    def sgpr_elbo(self, theta, noise: float, dZ: int, M: int, D: int, dX: int, derr: int, N: int, n_params: int,
+                  want_grad: bool, derrbar: Optional[int] = None) -> np.ndarray:
+        """[elbo, d/dnoise, d/dtheta (n_params), d/dZ (M*D)]; only [0] is meaningful without want_grad."""
+        out = np.zeros(2 + n_params + M * D, dtype=np.float64)
+        self._check(self._lib.gpb_sgpr_elbo(self._h, _as_dp(theta), float(noise), _P(dZ), M, D, _P(dX), _P(derr), N,
+                                            int(bool(want_grad)), out.ctypes.data_as(_DP), _P(derrbar)), "gpb_sgpr_elbo")
+        return out
+
+    def sgpr_predict_f(self, theta, noise: float, dZ: int, M: int, D: int, dX: int, derr: int, N: int, dXs: int, Ns: int,
+                       dmean: int, dvar: int):
+        self._check(self._lib.gpb_sgpr_predict_f(self._h, _as_dp(theta), float(noise), _P(dZ), M, D, _P(dX), _P(derr), N,
+                                                 _P(dXs), Ns, _P(dmean), _P(dvar)), "gpb_sgpr_predict_f")
 
     def adam_step(self, dx: int, dg: int, dm: int, dv: int, n: int, lr: float, step: int, beta1=0.9, beta2=0.999,
                   eps=1e-8, maximize: bool = True):

@@ -410,4 +410,22 @@ int gpb_svgp_predict_f(gpb_handle* h, const double* h_theta, const double* d_Z, 
     return svgp_predict_f(h, h_theta, d_Z, M, D, d_qmu, d_qsqrt, ldq, d_Xs, Ns, d_mean, d_var);
 }
 
+int gpb_sgpr_elbo(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z, int64_t M, int D,
+                  const double* d_X, const double* d_err, int64_t N, int want_grad, double* h_out, double* d_errbar) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Z || !d_X || !d_err || !h_out) return set_error(h, -2, "sgpr_elbo: null pointer");
+    if (M > 0x7fffffff || N > 0x7fffffff) return set_error(h, -2, "sgpr_elbo: size too large");
+    return sgpr_elbo(h, h_theta, noise_variance, d_Z, M, D, d_X, d_err, N, want_grad, h_out, d_errbar);
+}
+
+int gpb_sgpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Z, int64_t M, int D,
+                       const double* d_X, const double* d_err, int64_t N, const double* d_Xs, int64_t Ns, double* d_mean,
+                       double* d_var) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Z || !d_X || !d_err) return set_error(h, -2, "sgpr_predict_f: null pointer");
+    if (Ns > 0 && (!d_Xs || !d_mean || !d_var)) return set_error(h, -2, "sgpr_predict_f: null pointer");
+    if (M > 0x7fffffff || N > 0x7fffffff || Ns > 0x7fffffff) return set_error(h, -2, "sgpr_predict_f: size too large");
+    return sgpr_predict_f(h, h_theta, noise_variance, d_Z, M, D, d_X, d_err, N, d_Xs, Ns, d_mean, d_var);
+}
+
 }  // extern "C"

@@ -149,5 +149,9 @@ int svgp_finish(gpb_handle* h, double* d_flat, double scale, const double* d_qmu
                 int64_t M, int D, int P, int apply_grad, double* h_elbo, double* h_kl);
 int svgp_predict_f(gpb_handle* h, const double* theta, const double* d_Z, int64_t M, int D, const double* d_qmu,
                    const double* d_Lq, int64_t ldq, const double* d_Xs, int64_t Ns, double* d_mean, double* d_var);
+int sgpr_elbo(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D, const double* d_X,
+              const double* d_err, int64_t N, int want_grad, double* h_out, double* d_errbar);
+int sgpr_predict_f(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D, const double* d_X,
+                   const double* d_err, int64_t N, const double* d_Xs, int64_t Ns, double* d_mean, double* d_var);
 
 }  // namespace gpb

@@ -450,6 +450,64 @@ static int svgp_forward(gpb_handle* h, const DevKernel& kp, const double* d_Z, i
     return check_cuda(h, cudaGetLastError(), "svgp colstats launch");
 }
 
+// Shared tail of the SVGP and SGPR adjoints.  On entry s.Kuf holds Kuf_bar = d objective / d k(Z, X)
+// [M, B], s.A holds A = Wm k(Z, X), s.Kuu holds Lm (keepL) and s.Wm = Lm^-1; gv = d objective / d k(x_b, x_b).
+// Pulls the Cholesky adjoint back to Kuu_bar (the A = Lm^-1 Kuf dependence) and contracts Kuf_bar,
+// Kuu_bar and gv with dk/dtheta, dk/dz into g_theta [P] and g_Z [M, D] (overwritten).
+// scr: 4 M x ldm doubles (Lm_bar, Q, Sym, T1).
+static int sparse_backward_tail(gpb_handle* h, const DevKernel& kp, const double* d_Z, int64_t M, int D, const double* d_X,
+                                int64_t B, SvgpBuffers& s, double gv, double* scr, double* g_theta, double* g_Z) {
+    int rc;
+    GemmArgs g;
+    const int P = kp.n_params;
+    double* Lbar = scr;
+    double* Q = Lbar + (size_t)M * s.ldm;
+    double* Sym = Q + (size_t)M * s.ldm;
+    double* T1 = Sym + (size_t)M * s.ldm;
+    // Lm_bar = -tril(Kuf_bar A^T)
+    g = GemmArgs();
+    g.transa = 0; g.transb = 1; g.M = M; g.N = M; g.K = B; g.alpha = -1.0;
+    g.A = s.Kuf; g.lda = s.ldb; g.B = s.A; g.ldb = s.ldb; g.C = Lbar; g.ldc = s.ldm; g.tri = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    {
+        dim3 grid((unsigned)((M + 255) / 256), (unsigned)M);
+        zero_strict_upper_kernel<<<grid, 256, 0, h->stream>>>(Lbar, s.ldm, (int)M);
+        h->launches += 1;
+    }
+    // Q = Lm^T Lm_bar (lower tiles) ; Sym = sym-from-lower(Q)
+    g = GemmArgs();
+    g.transa = 1; g.transb = 0; g.M = M; g.N = M; g.K = M;
+    g.A = s.Kuu; g.lda = s.ldm; g.B = Lbar; g.ldb = s.ldm; g.C = Q; g.ldc = s.ldm; g.tri = 1; g.a_upper = 1; g.b_lower = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    {
+        dim3 grid((unsigned)((M + 255) / 256), (unsigned)M);
+        sym_from_lower_kernel<<<grid, 256, 0, h->stream>>>(Q, s.ldm, Sym, s.ldm, (int)M);
+        h->launches += 1;
+    }
+    // Kuu_bar = 1/2 Wm^T Sym Wm
+    g = GemmArgs();
+    g.transa = 0; g.transb = 0; g.M = M; g.N = M; g.K = M;
+    g.A = Sym; g.lda = s.ldm; g.B = s.Wm; g.ldb = s.ldm; g.C = T1; g.ldc = s.ldm; g.b_lower = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    double* Kuubar = Q;  // Q is dead
+    g = GemmArgs();
+    g.transa = 1; g.transb = 0; g.M = M; g.N = M; g.K = M; g.alpha = 0.5;
+    g.A = s.Wm; g.lda = s.ldm; g.B = T1; g.ldb = s.ldm; g.C = Kuubar; g.ldc = s.ldm; g.a_upper = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    // theta / Z gradients: Kuf_bar against k(Z, X); Kuu_bar against k(Z, Z) (both arguments -> factor 2); kdiag
+    if ((rc = cross_grad(h, kp, d_Z, M, d_X, B, D, s.Kuf, s.ldb, 1.0, g_theta, g_Z, 0))) return rc;
+    if ((rc = cross_grad(h, kp, d_Z, M, d_Z, M, D, Kuubar, s.ldm, 2.0, g_theta, g_Z, 1))) return rc;
+    {
+        const int nb = 2 * h->sm_count;
+        double* part = workspace(h, BUF_RED, (size_t)nb * GPB_MAX_PARAMS * sizeof(double));
+        if (!part) return -1;
+        SVGP_DISPATCH_DP(D, (kdiag_grad_kernel<DP><<<nb, 256, 0, h->stream>>>(kp, d_X, (int)B, D, gv, part)));
+        reduce_rows_kernel<<<P, 256, 0, h->stream>>>(part, nb, GPB_MAX_PARAMS, 1.0, g_theta, 1);
+        h->launches += 2;
+    }
+    return check_cuda(h, cudaGetLastError(), "sparse backward launches");
+}
+
 // q_sqrt must carry zeros above the diagonal inside 128-aligned diagonal blocks (engine convention);
 // the host layer passes tril(q_sqrt).
 int svgp_data_term(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D,
@@ -504,55 +562,9 @@ int svgp_data_term(gpb_handle* h, const double* theta, double s2, const double* 
     g.transa = 1; g.transb = 0; g.M = M; g.N = B; g.K = M;
     g.A = s.Wm; g.lda = s.ldm; g.B = s.G; g.ldb = s.ldb; g.C = s.Kuf; g.ldc = s.ldb; g.a_upper = 1;
     if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    // M x M scratch: Lm_bar, Q, Sym, T1
     double* scr = workspace(h, BUF_PANEL, (size_t)4 * M * s.ldm * sizeof(double));
     if (!scr) return -1;
-    double* Lbar = scr;
-    double* Q = Lbar + (size_t)M * s.ldm;
-    double* Sym = Q + (size_t)M * s.ldm;
-    double* T1 = Sym + (size_t)M * s.ldm;
-    // Lm_bar = -tril(Kuf_bar A^T)
-    g = GemmArgs();
-    g.transa = 0; g.transb = 1; g.M = M; g.N = M; g.K = B; g.alpha = -1.0;
-    g.A = s.Kuf; g.lda = s.ldb; g.B = s.A; g.ldb = s.ldb; g.C = Lbar; g.ldc = s.ldm; g.tri = 1;
-    if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    {
-        dim3 grid((unsigned)((M + 255) / 256), (unsigned)M);
-        zero_strict_upper_kernel<<<grid, 256, 0, h->stream>>>(Lbar, s.ldm, (int)M);
-        h->launches += 1;
-    }
-    // Q = Lm^T Lm_bar (lower tiles) ; Sym = sym-from-lower(Q)
-    g = GemmArgs();
-    g.transa = 1; g.transb = 0; g.M = M; g.N = M; g.K = M;
-    g.A = s.Kuu; g.lda = s.ldm; g.B = Lbar; g.ldb = s.ldm; g.C = Q; g.ldc = s.ldm; g.tri = 1; g.a_upper = 1; g.b_lower = 1;
-    if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    {
-        dim3 grid((unsigned)((M + 255) / 256), (unsigned)M);
-        sym_from_lower_kernel<<<grid, 256, 0, h->stream>>>(Q, s.ldm, Sym, s.ldm, (int)M);
-        h->launches += 1;
-    }
-    // Kuu_bar = 1/2 Wm^T Sym Wm
-    g = GemmArgs();
-    g.transa = 0; g.transb = 0; g.M = M; g.N = M; g.K = M;
-    g.A = Sym; g.lda = s.ldm; g.B = s.Wm; g.ldb = s.ldm; g.C = T1; g.ldc = s.ldm; g.b_lower = 1;
-    if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    double* Kuubar = Q;  // Q is dead
-    g = GemmArgs();
-    g.transa = 1; g.transb = 0; g.M = M; g.N = M; g.K = M; g.alpha = 0.5;
-    g.A = s.Wm; g.lda = s.ldm; g.B = T1; g.ldb = s.ldm; g.C = Kuubar; g.ldc = s.ldm; g.a_upper = 1;
-    if ((rc = launch_gemm(h, g, h->stream))) return rc;
-    // theta / Z gradients: Kuf_bar against k(Z, X); Kuu_bar against k(Z, Z) (both arguments -> factor 2); kdiag
-    if ((rc = cross_grad(h, kp, d_Z, M, d_X, B, D, s.Kuf, s.ldb, 1.0, g_theta, g_Z, 0))) return rc;
-    if ((rc = cross_grad(h, kp, d_Z, M, d_Z, M, D, Kuubar, s.ldm, 2.0, g_theta, g_Z, 1))) return rc;
-    {
-        const int nb = 2 * h->sm_count;
-        double* part = workspace(h, BUF_RED, (size_t)nb * GPB_MAX_PARAMS * sizeof(double));
-        if (!part) return -1;
-        SVGP_DISPATCH_DP(D, (kdiag_grad_kernel<DP><<<nb, 256, 0, h->stream>>>(kp, d_X, (int)B, D, gv, part)));
-        reduce_rows_kernel<<<P, 256, 0, h->stream>>>(part, nb, GPB_MAX_PARAMS, 1.0, g_theta, 1);
-        h->launches += 2;
-    }
-    return check_cuda(h, cudaGetLastError(), "svgp backward launches");
+    return sparse_backward_tail(h, kp, d_Z, M, D, d_X, B, s, gv, scr, g_theta, g_Z);
 }
 
 int svgp_finish(gpb_handle* h, double* d_flat, double scale, const double* d_qmu, const double* d_Lq, int64_t ldq,
@@ -610,6 +622,320 @@ int svgp_predict_f(gpb_handle* h, const double* theta, const double* d_Z, int64_
         return info;
     }
     return 0;
+}
+
+
+// ====================================================================================================
+// SGPR -- Titsias' collapsed sparse bound (gpflow/models/sgpr.py SGPR.elbo / predict_f), the model the
+// reference builds at test_scripts/SVGP.py:393-399 and trains with Scipy.
+// Shares Kuu / Kuf assembly, the blocked factorisation and the adjoint tail with SVGP.
+//
+// Forward (s = noise variance, err = y - m(X), jitter = 1e-6):
+//   Lm = chol(k(Z,Z) + jitter I), Wm = Lm^-1          V = Wm k(Z,X)                     [M,N]
+//   Bm = I + V V^T / s, LB = chol(Bm), WB = LB^-1     c = WB V err / s,  beta = WB^T c  (= Bm^-1 V err / s)
+//   elbo = -N/2 log 2pi - sum log LB_ii - N/2 log s - (sum_n kdiag_n - tr V V^T)/(2s) - |err|^2/(2s) + |c|^2/2
+// Adjoint (hand-derived; replaces TF autodiff through two Choleskys):
+//   H = I - Bm^-1 - beta beta^T                        V_bar = (H V + beta err^T) / s
+//   Kuf_bar = Wm^T V_bar ; Lm_bar, Kuu_bar and the theta / Z contractions: sparse_backward_tail
+//   d/dkdiag_n = -1/(2s) ; err_bar = (V^T beta - err) / s
+//   d/ds = [(M - tr Bm^-1)/2 - N/2 - (|c|^2 + |beta|^2)/2]/s + [sum kdiag - tr V V^T + |err|^2]/(2 s^2)
+// Three M x M x N products (V, V V^T lower, H-weighted V) plus the tail's one; M^3 work is minor.
+
+// out[0] = trace(B) before the shift (fixed order, one block); then B_ii += 1
+__global__ void sgpr_shift_trace_kernel(double* __restrict__ B, int64_t ld, int M, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += 256) {
+        const double d = B[(int64_t)i * ld + i];
+        s += d;
+        B[(int64_t)i * ld + i] = d + 1.0;
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// out[0] = sum a_i^2 (a may be null -> 0), out[1] = sum b_i (b may be null -> 0); one block, fixed order
+__global__ void sgpr_sums_kernel(const double* __restrict__ a, int64_t na, const double* __restrict__ b, int64_t nb,
+                                 double* __restrict__ out) {
+    __shared__ double sm[2][1024];
+    double sa = 0.0, sb = 0.0;
+    if (a) for (int64_t i = threadIdx.x; i < na; i += 1024) sa = fma(a[i], a[i], sa);
+    if (b) for (int64_t i = threadIdx.x; i < nb; i += 1024) sb += b[i];
+    sm[0][threadIdx.x] = sa;
+    sm[1][threadIdx.x] = sb;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) {
+            sm[0][threadIdx.x] += sm[0][threadIdx.x + k];
+            sm[1][threadIdx.x] += sm[1][threadIdx.x + k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sm[0][0]; out[1] = sm[1][0]; }
+}
+
+// out[0] = trace of a lower-stored matrix (one block, fixed order)
+__global__ void sgpr_trace_kernel(const double* __restrict__ A, int64_t ld, int M, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += 256) s += A[(int64_t)i * ld + i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+__global__ void scale_vec_kernel(double* __restrict__ v, int n, double a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= a;
+}
+
+// H = I - Binv - beta beta^T (full symmetric, from the lower-stored Binv)
+__global__ void sgpr_h_kernel(const double* __restrict__ Binv, int64_t ldb, int M, const double* __restrict__ beta,
+                              double* __restrict__ H, int64_t ldh) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= M) return;
+    const double bi = (i >= j) ? Binv[(int64_t)i * ldb + j] : Binv[(int64_t)j * ldb + i];
+    H[(int64_t)i * ldh + j] = ((i == j) ? 1.0 : 0.0) - bi - beta[i] * beta[j];
+}
+
+// G[m][b] += scale * w[m] * e[b]
+__global__ void rank1_add_kernel(double* __restrict__ G, int64_t ld, int M, int64_t N, const double* __restrict__ w,
+                                 const double* __restrict__ e, double scale) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (b >= N) return;
+    const int64_t o = (int64_t)m * ld + b;
+    G[o] = fma(scale * w[m], e[b], G[o]);
+}
+
+// out[b] = (sum_m V[m][b] beta[m] - err[b]) / s
+__global__ void sgpr_errbar_kernel(const double* __restrict__ V, int64_t ld, int M, int64_t N, const double* __restrict__ beta,
+                                   const double* __restrict__ err, double inv_s, double* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    double s = 0.0;
+    for (int m = 0; m < M; ++m) s = fma(V[(int64_t)m * ld + b], beta[m], s);
+    out[b] = (s - err[b]) * inv_s;
+}
+
+struct SgprState {
+    SvgpBuffers s;       // Kuu (-> Lm), Wm, Kuf, A (= V), ldm, ldb
+    double *Bm, *WB, *mm2, *mm3, *scr;   // M x ldm each; scr = 4 M x ldm for the tail
+    double *u, *c, *beta, *wbeta, *logdiagM, *logdiagB, *kdiag, *scal, *flat;
+    int *info;           // [0] Kuu, [1] Bm
+};
+
+static int sgpr_forward(gpb_handle* h, const DevKernel& kp, double s2, const double* d_Z, int64_t M, int D, const double* d_X,
+                        const double* d_err, int64_t N, bool want_grad, int P, SgprState* st) {
+    SvgpBuffers& s = st->s;
+    s.ldm = rup(M, 16);
+    s.ldb = rup(N, 16);
+    const size_t mat = (size_t)rup(M, 128) * s.ldm;
+    const size_t big = (size_t)M * s.ldb;
+    s.Kuu = workspace(h, BUF_K, mat * sizeof(double));
+    s.Wm = workspace(h, BUF_W, mat * sizeof(double));
+    s.Kuf = workspace(h, BUF_AUX, big * sizeof(double));
+    s.A = workspace(h, BUF_AUX2, big * sizeof(double));
+    const int64_t nbk = rup((M + 127) / 128, 16);
+    const size_t small = (size_t)(4 * s.ldm + 2 * nbk + s.ldb + 16 + 2 + P + M * D + 16);
+    double* v = workspace(h, BUF_VEC, small * sizeof(double));
+    if (!s.Kuu || !s.Wm || !s.Kuf || !s.A || !v) return -1;
+    st->u = v;
+    st->c = st->u + s.ldm;
+    st->beta = st->c + s.ldm;
+    st->wbeta = st->beta + s.ldm;
+    st->logdiagM = st->wbeta + s.ldm;
+    st->logdiagB = st->logdiagM + nbk;
+    st->kdiag = st->logdiagB + nbk;
+    st->scal = st->kdiag + s.ldb;    // [0] tr(VV^T)/s [1] |err|^2 [2] sum kdiag [3] |c|^2 [4] sum log LB [5] tr Bm^-1 [6] |beta|^2
+    st->flat = st->scal + 16;        // [2 + P + M D]
+    st->info = reinterpret_cast<int*>(st->flat + 2 + P + M * D);
+    int rc;
+    if ((rc = launch_assemble(h, kp, d_Z, M, d_Z, M, D, s.Kuu, s.ldm, 1, 1e-6))) return rc;   // default_jitter
+    if ((rc = factor_inv(h, s.Kuu, s.ldm, s.Wm, s.ldm, M, st->logdiagM, st->info, want_grad))) return rc;
+    // persistent M x M scratch is taken only now: factor_inv(keepL) borrows BUF_PANEL while it runs
+    double* mm = workspace(h, BUF_PANEL, (size_t)(4 * mat + 4 * (size_t)M * s.ldm) * sizeof(double));
+    if (!mm) return -1;
+    st->Bm = mm;
+    st->WB = mm + mat;
+    st->mm2 = mm + 2 * mat;
+    st->mm3 = mm + 3 * mat;
+    st->scr = mm + 4 * mat;
+    if ((rc = launch_assemble(h, kp, d_Z, M, d_X, N, D, s.Kuf, s.ldb, 0, 0.0))) return rc;
+    if ((rc = launch_kdiag(h, kp, d_X, N, D, st->kdiag))) return rc;
+    GemmArgs g;
+    g.transa = 0; g.transb = 0; g.M = M; g.N = N; g.K = M;          // V = Wm Kuf
+    g.A = s.Wm; g.lda = s.ldm; g.B = s.Kuf; g.ldb = s.ldb; g.C = s.A; g.ldc = s.ldb; g.a_lower = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    g = GemmArgs();
+    g.transa = 0; g.transb = 1; g.M = M; g.N = M; g.K = N; g.alpha = 1.0 / s2;   // Bm - I = V V^T / s (lower tiles)
+    g.A = s.A; g.lda = s.ldb; g.B = s.A; g.ldb = s.ldb; g.C = st->Bm; g.ldc = s.ldm; g.tri = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    sgpr_shift_trace_kernel<<<1, 256, 0, h->stream>>>(st->Bm, s.ldm, (int)M, st->scal + 0);
+    sgpr_sums_kernel<<<1, 1024, 0, h->stream>>>(d_err, N, st->kdiag, N, st->scal + 1);
+    h->launches += 2;
+    if ((rc = factor_inv(h, st->Bm, s.ldm, st->WB, s.ldm, M, st->logdiagB, st->info + 1, false))) return rc;
+    rowdot_kernel<<<(unsigned)((M + 7) / 8), 256, 0, h->stream>>>(s.A, s.ldb, (int)M, (int)N, d_err, st->u);   // u = V err
+    h->launches += 1;
+    if ((rc = trmv_lower(h, st->WB, s.ldm, M, st->u, st->c))) return rc;
+    scale_vec_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(st->c, (int)M, 1.0 / s2);              // c = WB u / s
+    h->launches += 1;
+    if ((rc = trmv_lower_T(h, st->WB, s.ldm, M, st->c, st->beta))) return rc;                                  // beta = WB^T c
+    if ((rc = quad_logdet(h, st->c, M, st->logdiagB, st->scal + 3))) return rc;                               // |c|^2, sum log LB
+    return check_cuda(h, cudaGetLastError(), "sgpr forward launches");
+}
+
+static int sgpr_check_info(gpb_handle* h, const int* info) {
+    if (info[0] > 0) {
+        set_error(h, info[0], "Cholesky decomposition was not successful: Kuu pivot %d", info[0]);
+        return info[0];
+    }
+    if (info[1] > 0) {
+        set_error(h, info[1], "Cholesky decomposition was not successful: I + A A^T pivot %d", info[1]);
+        return info[1];
+    }
+    return 0;
+}
+
+// h_out [2 + P + M*D] = elbo, d elbo/d noise, d elbo/d theta (constrained), d elbo/d Z (row-major);
+// d_errbar [N] (optional) = d elbo / d err (the host layer chains it through the mean function).
+int sgpr_elbo(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D, const double* d_X,
+              const double* d_err, int64_t N, int want_grad, double* h_out, double* d_errbar) {
+    if (!h->has_spec) return set_error(h, -3, "sgpr: no kernel set");
+    if (M <= 0 || N <= 0) return set_error(h, -2, "sgpr: empty problem");
+    if (!(s2 > 0.0)) return set_error(h, -2, "sgpr: noise variance must be > 0");
+    DevKernel kp;
+    int rc = build_dev_kernel(h, theta, &kp);
+    if (rc) return rc;
+    if (kp.n_dims != D) return set_error(h, -2, "sgpr: kernel expects D=%d, got %d", kp.n_dims, D);
+    if (want_grad && (kp.n_leaves > GRAD_FAST_LEAVES || kp.has_ard))
+        return set_error(h, -4, "sgpr gradient supports kernels with <= %d leaves and scalar lengthscales", GRAD_FAST_LEAVES);
+    const int P = kp.n_params;
+    SgprState st;
+    if ((rc = sgpr_forward(h, kp, s2, d_Z, M, D, d_X, d_err, N, want_grad != 0, P, &st))) return rc;
+    SvgpBuffers& s = st.s;
+    const size_t nflat = (size_t)(2 + P + M * D);
+    if (want_grad) {
+        double* g_theta = st.flat + 2;
+        double* g_Z = g_theta + P;
+        // Bm^-1 = WB^T WB (lower tiles) ; H = I - Bm^-1 - beta beta^T
+        if ((rc = lauum_lower(h, st.WB, M, s.ldm, st.mm2, s.ldm))) return rc;
+        sgpr_trace_kernel<<<1, 256, 0, h->stream>>>(st.mm2, s.ldm, (int)M, st.scal + 5);
+        sgpr_sums_kernel<<<1, 1024, 0, h->stream>>>(st.beta, M, nullptr, 0, st.scal + 6);
+        {
+            dim3 grid((unsigned)((M + 255) / 256), (unsigned)M);
+            sgpr_h_kernel<<<grid, 256, 0, h->stream>>>(st.mm2, s.ldm, (int)M, st.beta, st.mm3, s.ldm);
+        }
+        h->launches += 3;
+        // G1 = Wm^T H  (into the dead Bm buffer) ; Kuf_bar = G1 V / s + (Wm^T beta) err^T / s
+        GemmArgs g;
+        g.transa = 1; g.transb = 0; g.M = M; g.N = M; g.K = M;
+        g.A = s.Wm; g.lda = s.ldm; g.B = st.mm3; g.ldb = s.ldm; g.C = st.Bm; g.ldc = s.ldm; g.a_upper = 1;
+        if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        g = GemmArgs();
+        g.transa = 0; g.transb = 0; g.M = M; g.N = N; g.K = M; g.alpha = 1.0 / s2;
+        g.A = st.Bm; g.lda = s.ldm; g.B = s.A; g.ldb = s.ldb; g.C = s.Kuf; g.ldc = s.ldb;
+        if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        if ((rc = trmv_lower_T(h, s.Wm, s.ldm, M, st.beta, st.wbeta))) return rc;
+        {
+            dim3 grid((unsigned)((N + 255) / 256), (unsigned)M);
+            rank1_add_kernel<<<grid, 256, 0, h->stream>>>(s.Kuf, s.ldb, (int)M, N, st.wbeta, d_err, 1.0 / s2);
+            h->launches += 1;
+        }
+        if (d_errbar) {
+            sgpr_errbar_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(s.A, s.ldb, (int)M, N, st.beta, d_err,
+                                                                                   1.0 / s2, d_errbar);
+            h->launches += 1;
+        }
+        if ((rc = sparse_backward_tail(h, kp, d_Z, M, D, d_X, N, s, -0.5 / s2, st.scr, g_theta, g_Z))) return rc;
+    }
+    // one D2H of the scalars, the gradient record and the two pivot flags; the only sync of the evaluation
+    double* hp = pinned(h, (nflat + 16 + 2) * sizeof(double));
+    if (!hp) return -1;
+    cudaError_t e = cudaMemcpyAsync(hp, st.scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && want_grad)
+        e = cudaMemcpyAsync(hp + 16, st.flat, nflat * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hp + 16 + nflat, st.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "sgpr result copy/sync");
+    if ((rc = sgpr_check_info(h, reinterpret_cast<int*>(hp + 16 + nflat)))) return rc;
+    const double trVV = s2 * hp[0], ee = hp[1], sk = hp[2], cc = hp[3], hl = hp[4];
+    h_out[0] = -0.5 * (double)N * log(2.0 * M_PI) - hl - 0.5 * (double)N * log(s2) - 0.5 * (sk - trVV) / s2 - 0.5 * ee / s2 +
+               0.5 * cc;
+    if (want_grad) {
+        const double trBinv = hp[5], bb = hp[6];
+        h_out[1] = (0.5 * ((double)M - trBinv) - 0.5 * (double)N - 0.5 * (cc + bb)) / s2 + 0.5 * (sk - trVV + ee) / (s2 * s2);
+        for (size_t i = 2; i < nflat; ++i) h_out[i] = hp[16 + i];
+    }
+    return 0;
+}
+
+// SGPR.predict_f(Xnew, full_cov=False): mean = tmp2^T c, var = k** + |tmp2|^2 - |tmp1|^2 with
+// tmp1 = Wm k(Z, Xnew), tmp2 = WB tmp1 (mean excludes mean_function(Xnew)).
+int sgpr_predict_f(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D, const double* d_X,
+                   const double* d_err, int64_t N, const double* d_Xs, int64_t Ns, double* d_mean, double* d_var) {
+    if (!h->has_spec) return set_error(h, -3, "sgpr: no kernel set");
+    if (M <= 0 || N <= 0) return set_error(h, -2, "sgpr: empty problem");
+    if (!(s2 > 0.0)) return set_error(h, -2, "sgpr: noise variance must be > 0");
+    if (Ns <= 0) return 0;
+    DevKernel kp;
+    int rc = build_dev_kernel(h, theta, &kp);
+    if (rc) return rc;
+    if (kp.n_dims != D) return set_error(h, -2, "sgpr: kernel expects D=%d, got %d", kp.n_dims, D);
+    SgprState st;
+    if ((rc = sgpr_forward(h, kp, s2, d_Z, M, D, d_X, d_err, N, false, kp.n_params, &st))) return rc;
+    SvgpBuffers& s = st.s;
+    // the [M, N] training buffers are dead now: reuse them for the test chunks
+    int64_t chunk = (int64_t)(1 << 26) / M / 128 * 128;
+    if (chunk < 128) chunk = 128;
+    if (chunk > Ns) chunk = rup(Ns, 16);
+    const int64_t ldc = rup(chunk, 16);
+    double* Kus = workspace(h, BUF_AUX, (size_t)M * ldc * sizeof(double));
+    double* t1 = workspace(h, BUF_AUX2, (size_t)M * ldc * sizeof(double));
+    const int nch = (int)((M + CS_CH - 1) / CS_CH);
+    double* t2 = workspace(h, BUF_RED, ((size_t)M * ldc + 3 * (size_t)nch * chunk + 3 * (size_t)ldc) * sizeof(double));
+    if (!Kus || !t1 || !t2) return -1;
+    double* cpart = t2 + (size_t)M * ldc;
+    double* kd = cpart + 3 * (size_t)nch * chunk;
+    double* fm = kd + ldc;
+    double* fv = fm + ldc;
+    for (int64_t s0 = 0; s0 < Ns; s0 += chunk) {
+        const int64_t m = (Ns - s0 < chunk) ? (Ns - s0) : chunk;
+        const double* Xs = d_Xs + s0 * D;
+        if ((rc = launch_assemble(h, kp, d_Z, M, Xs, m, D, Kus, ldc, 0, 0.0))) return rc;
+        if ((rc = launch_kdiag(h, kp, Xs, m, D, kd))) return rc;
+        GemmArgs g;
+        g.transa = 0; g.transb = 0; g.M = M; g.N = m; g.K = M;
+        g.A = s.Wm; g.lda = s.ldm; g.B = Kus; g.ldb = ldc; g.C = t1; g.ldc = ldc; g.a_lower = 1;
+        if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        g.A = st.WB; g.B = t1; g.C = t2;
+        if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        dim3 grid((unsigned)((m + 127) / 128), (unsigned)nch);
+        colstats_partial_kernel<<<grid, 128, 0, h->stream>>>(t1, t2, ldc, (int)M, (int)m, st.beta, cpart, cpart + (size_t)nch * m,
+                                                             cpart + 2 * (size_t)nch * m);
+        colstats_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(
+            cpart, cpart + (size_t)nch * m, cpart + 2 * (size_t)nch * m, nch, (int)m, kd, nullptr, 1.0, fm, fv, nullptr, nullptr);
+        h->launches += 2;
+        cudaError_t e = cudaMemcpyAsync(d_mean + s0, fm, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_var + s0, fv, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) return check_cuda(h, e, "sgpr predict copy");
+    }
+    double* hp = pinned(h, (size_t)(64 + 2) * sizeof(double));
+    if (!hp) return -1;
+    cudaError_t e = cudaMemcpyAsync(hp + 64, st.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "sgpr predict sync");
+    return sgpr_check_info(h, reinterpret_cast<int*>(hp + 64));
 }
 
 }  // namespace gpb

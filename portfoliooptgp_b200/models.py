@@ -382,3 +382,100 @@ class SVGP(GPModel):
         eng.svgp_predict_f(ck.theta(), Z.data_ptr(), M, D, qmu.data_ptr(), Lq.data_ptr(), M, Xs.data_ptr(), Ns,
                            out[0].data_ptr(), out[1].data_ptr())
         return _out(out[0][:, None]), _out(out[1][:, None])
+
+
+class SGPR(GPModel):
+    """Sparse GP regression with Titsias' collapsed bound (gpflow/models/sgpr.py), as constructed at
+    test_scripts/SVGP.py:393-399: ``SGPR((X, Y), kernel, inducing_variable=Z)`` trained with Scipy on
+    ``training_loss`` and queried with ``predict_y``.  The bound, its hand-derived adjoint w.r.t.
+    kernel hyper-parameters, noise variance, inducing points and mean-function output, and predict_f
+    run on the device (csrc/svgp.cu, gpb_sgpr_*)."""
+
+    def __init__(self, data, kernel: Kernel, inducing_variable, *, mean_function: Optional[MeanFunction] = None,
+                 num_latent_gps: Optional[int] = None, noise_variance: Optional[float] = None,
+                 likelihood: Optional[Gaussian] = None, device=None):
+        if likelihood is not None and noise_variance is not None:
+            raise ValueError("only one of noise_variance and likelihood may be given")
+        if likelihood is None:
+            likelihood = Gaussian(1.0 if noise_variance is None else noise_variance)
+        if num_latent_gps not in (None, 1):
+            raise NotImplementedError("only single-output Y [N,1] is supported")
+        super().__init__(kernel, likelihood, mean_function, device)
+        X, Y = data
+        Xd = ops.to_device(X, self._device_index, ndim=2)
+        Yd = ops.to_device(Y, self._device_index, ndim=2)
+        if Xd.shape[0] != Yd.shape[0]:
+            raise ValueError(f"X has {Xd.shape[0]} rows, Y has {Yd.shape[0]}")
+        if Yd.shape[1] != 1:
+            raise NotImplementedError("only single-output Y [N,1] is supported (R = 1 on every reference call site)")
+        self.data = (Xd, Yd)
+        self.num_latent_gps = 1
+        self.inducing_variable = inducing_variable if isinstance(inducing_variable, InducingPoints) else InducingPoints(inducing_variable)
+        if self.inducing_variable.Z.shape[1] != Xd.shape[1]:
+            raise ValueError(f"Z has {self.inducing_variable.Z.shape[1]} columns, X has {Xd.shape[1]}")
+
+    def _children(self):
+        for key, val in super()._children():
+            if key != "num_latent_gps":
+                yield key, val
+
+    def _inputs(self):
+        Xd, Yd = self.data
+        eng = self._get_engine()
+        ck = self._lower_kernel(Xd.shape[1])
+        err = Yd[:, 0] if isinstance(self.mean_function, Zero) else (Yd - self.mean_function(Xd))[:, 0]
+        Z = torch.from_numpy(np.ascontiguousarray(self.inducing_variable.Z.numpy())).to(Xd.device)
+        return eng, ck, Xd, err.contiguous(), Z
+
+    def _noise(self) -> float:
+        return float(self.likelihood.variance.numpy())
+
+    def elbo(self):
+        eng, ck, Xd, err, Z = self._inputs()
+        M, D = Z.shape
+        out = eng.sgpr_elbo(ck.theta(), self._noise(), Z.data_ptr(), M, D, Xd.data_ptr(), err.data_ptr(), Xd.shape[0],
+                            ck.n_params, False)
+        return torch.tensor(out[0], dtype=torch.float64)
+
+    def maximum_log_likelihood_objective(self):
+        return self.elbo()
+
+    def _mll(self, data):
+        if data is not None:
+            raise ValueError("SGPR holds its data internally; training_loss takes no data")
+        return self.elbo()
+
+    def _training_loss_and_grads(self, variables: Sequence[Variable], data=None):
+        eng, ck, Xd, err, Z = self._inputs()
+        M, D = Z.shape
+        N = Xd.shape[0]
+        train_mean = any(p.trainable for p in self.mean_function.parameters)
+        errbar = torch.empty(N, dtype=torch.float64, device=Xd.device) if train_mean else None
+        out = eng.sgpr_elbo(ck.theta(), self._noise(), Z.data_ptr(), M, D, Xd.data_ptr(), err.data_ptr(), N, ck.n_params,
+                            True, None if errbar is None else errbar.data_ptr())
+        P = ck.n_params
+        by_param = ck.scatter_grad(out[2:2 + P])
+        pv = self.likelihood.variance
+        by_param[id(pv)] = np.asarray(out[1]) * pv.transform.forward_grad(pv.unconstrained_variable._value)
+        by_param[id(self.inducing_variable.Z)] = out[2 + P:].reshape(M, D)
+        if train_mean:
+            # err = Y - m(X): d elbo/d m(X) = -err_bar
+            by_param.update(self.mean_function.backward(Xd, -errbar))
+        return -out[0], self._grads_for(variables, by_param, -1.0)
+
+    def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):
+        if full_cov or full_output_cov:
+            raise NotImplementedError("predict_f(full_cov=True) is not on the reference path")
+        eng, ck, Xd, err, Z = self._inputs()
+        M, D = Z.shape
+        Xs = ops.to_device(Xnew, self._device_index, ndim=2)
+        if Xs.shape[1] != D:
+            raise ValueError(f"Xnew has {Xs.shape[1]} columns, the model was built with {D}")
+        Ns = Xs.shape[0]
+        out = torch.empty((2, Ns), dtype=torch.float64, device=Xs.device)
+        eng.sgpr_predict_f(ck.theta(), self._noise(), Z.data_ptr(), M, D, Xd.data_ptr(), err.data_ptr(), Xd.shape[0],
+                           Xs.data_ptr(), Ns, out[0].data_ptr(), out[1].data_ptr())
+        mean = out[0][:, None]
+        if not isinstance(self.mean_function, Zero):
+            mean = mean + self.mean_function(Xs)
+        return _out(mean), _out(out[1][:, None])
