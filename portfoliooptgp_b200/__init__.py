@@ -15,3 +15,5 @@ from ._capi import CholeskyError, EngineError  # noqa: F401
 __version__ = "0.1.0"
 from . import batched  # noqa: E402,F401
 from .batched import BatchedGPR, lockstep_lbfgsb  # noqa: E402,F401
+from . import data_prep, postprocess  # noqa: E402,F401
+from . import mean_functions as functions  # noqa: E402,F401  (gpflow.functions alias)
