@@ -67,51 +67,70 @@ __device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const doub
 // replaced by 1 so that no NaNs propagate.
 // (a) one warp, every lane redundantly: factor the 8x8 diagonal block at (p, p) in registers, invert the
 // factor, store L_pp (zero strict upper) and M = L_pp^-1.
+// 1/sqrt(d) for d > 0 in the normal range, branch-free: MUFU.RSQ64H seed (>= 20 bits) and one cubic
+// correction y (1 + e/2 + 3 e^2/8), e = 1 - d y^2  (|y^2 d - 1| <= 3e-16 measured, tools/lat_bench.cu;
+// 5 dependent FP64 ops, no slow-path call as in the library rsqrt).  d = +inf / NaN give NaN, which the
+// next pivot test flags.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d * y, y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
+
 __device__ __forceinline__ void warp_diag_factor(double* S, int p, int* fail, double* M) {
+    // One straight-line block (a single warp runs it, so issue latency per instruction is what
+    // counts): every lane holds the whole lower triangle in registers (broadcast LDS.128), the pivot
+    // chain d_j -> rsqrt -> scale -> d_j+1 is the critical path, and the rank-1 updates plus the rows
+    // of the inverse (all entries, static register indices, no selects) fill its latency bubbles.
     const int lane = threadIdx.x & 31;
-    double a[8][8];
+    double a[8][8], m[8][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) a[r][c] = S[(p + r) * SLD + p + c];
-    double rs[8];
+    unsigned bad = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         double d = a[j][j];
-        if (!(d > 0.0)) {
-            if (lane == 0 && *fail == 0) *fail = p + j + 1;
-            d = 1.0;
-        }
-        rs[j] = rsqrt(d);
-        a[j][j] = d * rs[j];
+        const bool ok = d > 0.0;
+        bad |= ok ? 0u : (1u << j);
+        d = ok ? d : 1.0;
+        const double rs = rsqrt_pos(d);
+        a[j][j] = d * rs;
 #pragma unroll
-        for (int r = j + 1; r < 8; ++r) a[r][j] *= rs[j];
+        for (int r = j + 1; r < 8; ++r) a[r][j] *= rs;
 #pragma unroll
         for (int r = j + 1; r < 8; ++r)
 #pragma unroll
             for (int k = j + 1; k <= r; ++k) a[r][k] = fma(-a[r][j], a[k][j], a[r][k]);
-    }
-    // inverse of the factor: lane c (mod 8) solves column c; 1/L_jj = rs[j]
-    double x[8];
-    const int c = lane & 7;
+        // row j of the inverse: m_jj = 1/L_jj, m_jc = -m_jj sum_{k=c}^{j-1} L_jk m_kc (newest m last)
+        m[j][j] = rs;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        double v = (r == c) ? 1.0 : 0.0;
+        for (int c = 0; c < j; ++c) {
+            double s = a[j][c] * m[c][c];
 #pragma unroll
-        for (int k = 0; k < r; ++k) v = fma(-a[r][k], x[k], v);
-        x[r] = (r >= c) ? v * rs[r] : 0.0;
-    }
-    // write back: lane r (< 8) writes row r of L (static register indices via the unrolled select)
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        if (lane == r) {
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) S[(p + r) * SLD + p + cc] = (cc <= r) ? a[r][cc] : 0.0;
+            for (int k = c + 1; k < j; ++k) s = fma(a[j][k], m[k][c], s);
+            m[j][c] = -s * rs;
         }
     }
-    if (lane < 8) {
+    if (lane == 0) {
+        if (bad != 0u && *fail == 0) *fail = p + __ffs(bad);
+        // L_pp with an explicit zero strict upper part (the trailing updates left symmetric garbage
+        // there); the inverse block keeps the zeros dinv was initialised with above the diagonal
 #pragma unroll
-        for (int r = 0; r < 8; ++r) M[r * DLD + c] = x[r];
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const double v0 = (2 * h <= r) ? a[r][2 * h] : 0.0, v1 = (2 * h + 1 <= r) ? a[r][2 * h + 1] : 0.0;
+                *reinterpret_cast<double2*>(S + (p + r) * SLD + p + 2 * h) = make_double2(v0, v1);
+            }
+#pragma unroll
+            for (int h = 0; 2 * h <= r; ++h) {
+                const double v1 = (2 * h + 1 <= r) ? m[r][2 * h + 1] : 0.0;
+                *reinterpret_cast<double2*>(M + r * DLD + 2 * h) = make_double2(m[r][2 * h], v1);
+            }
+        }
     }
 }
 
@@ -132,6 +151,7 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
     if (tid == 0) *fail = 0;
+    for (int e = tid; e < (np >> 3) * 8 * DLD; e += nt) dinv[e] = 0.0;   // warp_diag_factor writes the lower parts only
     __syncthreads();
     if (warp == 0) warp_diag_factor(S, 0, fail, dinv);
     __syncthreads();

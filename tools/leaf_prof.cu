@@ -118,6 +118,51 @@ __global__ void __launch_bounds__(512) prof_kernel(const double* A, int n, long 
     if (tid == 0) { stamps[0] = t1 - t0; stamps[1] = t2 - t1; stamps[2] = t3 - t2; stamps[3] = t4 - t3; stamps[4] = tacc[0]; stamps[5] = tacc[1]; stamps[6] = tacc[2]; }
 }
 
+// current production routines + isolated sub-phases (16 sequential diagonal factors; one full panel
+// product; one full trailing update at p = 0)
+__global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long long* stamps) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm; double* T = sm + 128 * SLD; double* dinv = T + 64 * TLD; int* fail = (int*)(dinv + DINV_DOUBLES);
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) S[i * SLD + j] = (j <= i) ? A[i * n + j] : 0.0; }
+    __syncthreads();
+    long long t0 = clock64();
+    block_potrf_lower(S, n, fail, dinv);
+    long long t1 = clock64();
+    block_trtri_lower_inplace(S, n, T, dinv);
+    __syncthreads();
+    long long t2 = clock64();
+    // reload, then 16 diagonal factors back to back on warp 0 (values are garbage after the first; timing only)
+    for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) S[i * SLD + j] = (j <= i) ? A[i * n + j] : 0.0; }
+    __syncthreads();
+    long long t3 = clock64();
+    if (warp == 0) for (int p = 0; p < n; p += 8) { warp_diag_factor(S, p, fail, dinv + (p >> 3) * 8 * DLD); __syncwarp(); }
+    __syncthreads();
+    long long t4 = clock64();
+    {   // one panel product at p = 0
+        const int p = 0; const double* M = dinv; const int mt = (n - 8) >> 3;
+        for (int ti = warp; ti < mt; ti += nwarps) {
+            double* Pt = S + (p + 8 + ti * 8) * SLD + p;
+            double c0 = 0.0, c1 = 0.0;
+            warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+            __syncwarp();
+            *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
+        }
+    }
+    __syncthreads();
+    long long t5 = clock64();
+    {   // one trailing update at p = 0, all warps
+        const int mt = (n - 8) >> 3, ntiles = mt * (mt + 1) / 2;
+        for (int t = warp; t < ntiles; t += nwarps) warp_trailing_tile(S, 0, t);
+    }
+    __syncthreads();
+    long long t6 = clock64();
+    for (int i = 0; i < 16; ++i) __syncthreads();
+    long long t7 = clock64();
+    if (tid == 0) { stamps[0] = t1 - t0; stamps[1] = t2 - t1; stamps[2] = t4 - t3; stamps[3] = t5 - t4; stamps[4] = t6 - t5; stamps[5] = (t7 - t6) / 16; }
+}
+
 // isolated micro-latencies
 __global__ void lat_kernel(long long* out, double x) {
     double v = x; long long t0 = clock64();
@@ -151,6 +196,13 @@ int main() {
         for (int rep = 0; rep < 2; ++rep) prof_kernel<<<1, threads, smem>>>(dA, n, dS, dO);
         long long st[7]; cudaMemcpy(st, dS, 56, cudaMemcpyDeviceToHost);
         printf("threads %d cycles: load %lld potrf %lld [a %lld b %lld c %lld] trtri %lld store %lld (err %s)\n", threads, st[0], st[1], st[4], st[5], st[6], st[2], st[3], cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFuncSetAttribute(prof2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int threads : {256, 512}) {
+        for (int rep = 0; rep < 2; ++rep) prof2_kernel<<<1, threads, smem>>>(dA, n, dS);
+        long long st[6]; cudaMemcpy(st, dS, 48, cudaMemcpyDeviceToHost);
+        printf("current, threads %d cycles: potrf %lld trtri %lld | 16 diag factors %lld, panel product(p=0) %lld, trailing(p=0) %lld, syncthreads %lld (err %s)\n",
+               threads, st[0], st[1], st[2], st[3], st[4], st[5], cudaGetErrorString(cudaGetLastError()));
     }
     lat_kernel<<<1, 32>>>(dS, 1.3);
     long long l[7]; cudaMemcpy(l, dS, 56, cudaMemcpyDeviceToHost);
