@@ -16,6 +16,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// phase-timing hooks for tools/leaf_prof.cu (compiled out everywhere else)
+#ifndef GPB_POTRF_STAMP
+#define GPB_POTRF_DECL
+#define GPB_POTRF_STAMP(i)
+#endif
+
 namespace gpb {
 
 constexpr int SLD = 132;          // shared-memory leading dimension (doubles)
@@ -50,6 +56,31 @@ __device__ __forceinline__ void warp_tile_mma(double& c0, double& c1, const doub
         const double a = sign * ap[k * sak];
         const double b = bp[k * sbk];
         dmma_8x8x4(c0, c1, a, b);
+    }
+}
+
+// 2x2 register blocking of the same product: c[ri][rj] (four 8x8 tiles of a 16x16 block) +=
+// sign * A_ri[8 x (k1-k0)] * B_rj[(k1-k0) x 8], A tile ri at A + ri*8*sam, B tile rj at B + rj*8*sbn.
+// Four independent DMMA accumulator chains per warp and half the fragment loads per tile: the
+// in-shared-memory routines are bound by DMMA / LDS latency, not by throughput (tools/leaf_prof.cu).
+// a0, a1, b0, b1 (warp-uniform) switch tiles off: their fragments are not loaded and their products
+// are skipped -- used for ragged edges and for the k-ranges of triangular operands.
+__device__ __forceinline__ void warp_mma_2x2(double (&c)[2][2][2], const double* A, int sam, int sak, const double* B,
+                                             int sbk, int sbn, int k0, int k1, double sign, bool a0, bool a1, bool b0,
+                                             bool b1) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const double* ap0 = A + g * sam + q * sak;
+    const double* ap1 = ap0 + 8 * sam;
+    const double* bp0 = B + q * sbk + g * sbn;
+    const double* bp1 = bp0 + 8 * sbn;
+#pragma unroll 2
+    for (int k = k0; k < k1; k += 4) {
+        const double x0 = a0 ? sign * ap0[k * sak] : 0.0, x1 = a1 ? sign * ap1[k * sak] : 0.0;
+        const double y0 = b0 ? bp0[k * sbk] : 0.0, y1 = b1 ? bp1[k * sbk] : 0.0;
+        if (a0 && b0) dmma_8x8x4(c[0][0][0], c[0][0][1], x0, y0);
+        if (a0 && b1) dmma_8x8x4(c[0][1][0], c[0][1][1], x0, y1);
+        if (a1 && b0) dmma_8x8x4(c[1][0][0], c[1][0][1], x1, y0);
+        if (a1 && b1) dmma_8x8x4(c[1][1][0], c[1][1][1], x1, y1);
     }
 }
 
@@ -155,36 +186,92 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
     __syncthreads();
     if (warp == 0) warp_diag_factor(S, 0, fail, dinv);
     __syncthreads();
+    GPB_POTRF_DECL
     for (int p = 0; p + 8 < np; p += 8) {
         const double* M = dinv + (p >> 3) * 8 * DLD;
         const int mt = (np - p - 8) >> 3;
-        // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
-        for (int ti = warp; ti < mt; ti += nwarps) {
+        GPB_POTRF_STAMP(0)
+        // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores).
+        // With more than one warp, warp 0 owns the critical chain and never waits inside a step:
+        // panel tile 0 -> update of the next diagonal block -> its factorisation; it only ARRIVES at the
+        // named barrier that publishes panel tile 0 to the warps applying the rest of the update.
+        auto panel_tile = [&](int ti) {
             double* Pt = S + (p + 8 + ti * 8) * SLD + p;
             double c0 = 0.0, c1 = 0.0;
             warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
             __syncwarp();
             *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
+        };
+        if (nwarps > 1) {
+            if (warp == 0) {
+                panel_tile(0);
+                asm volatile("bar.arrive 1, %0;" ::"r"(nt) : "memory");
+                GPB_POTRF_STAMP(1)
+            } else {
+                for (int ti = warp; ti < mt; ti += nwarps - 1) panel_tile(ti);
+                GPB_POTRF_STAMP(1)
+                asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
+                GPB_POTRF_STAMP(2)
+            }
+        } else {
+            for (int ti = 0; ti < mt; ++ti) panel_tile(ti);
+            __syncwarp();
         }
-        __syncthreads();
         // (c) trailing update C -= P_ti P_tj^T over the 8x8 tiles (ti >= tj) of the trailing matrix, with
         // look-ahead: warp 0 updates the next diagonal block (tile 0) and factors it at once, while the
         // other warps apply the rest of the update.
         const int ntiles = mt * (mt + 1) / 2;
         if (nwarps > 1) {
             if (warp == 0) {
+                __syncwarp();
                 warp_trailing_tile(S, p, 0);
                 __syncwarp();
+                GPB_POTRF_STAMP(2)
                 warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
-            } else {
-                for (int t = warp; t < ntiles; t += nwarps - 1) warp_trailing_tile(S, p, t);
+                GPB_POTRF_STAMP(3)
+            } else if ((warp & 3) != 0) {
+                // 16x16 super-tiles (I >= J) of the trailing tile grid, one per warp and round; tile (0,0)
+                // belongs to warp 0, tiles above the diagonal or past the edge are neither loaded nor stored.
+                // Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe (DMMA and DFMA issue to the same
+                // unit): they sit this phase out so that the pivot chain runs uncontended (measured:
+                // the in-situ diagonal factor was 35 % slower than the isolated one, tools/leaf_prof.cu).
+                const int o = p + 8, st = (mt + 1) >> 1, nst = st * (st + 1) / 2;
+                const int aw = warp - 1 - (warp >> 2), naw = nwarps - ((nwarps + 3) >> 2);
+                for (int t = aw; t < nst; t += naw) {
+                    int I, J;
+                    tri_tile(t, I, J);
+                    const int ti0 = 2 * I, tj0 = 2 * J;
+                    const bool a1 = ti0 + 1 < mt, b1 = (J < I) || a1;
+                    const bool v[2][2] = {{!(I == 0 && J == 0), J < I}, {a1, a1}};
+                    double c[2][2][2];
+#pragma unroll
+                    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                        for (int rj = 0; rj < 2; ++rj) {
+                            double2 cc = make_double2(0.0, 0.0);
+                            if (v[ri][rj]) cc = *reinterpret_cast<const double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q);
+                            c[ri][rj][0] = cc.x;
+                            c[ri][rj][1] = cc.y;
+                        }
+                    warp_mma_2x2(c, S + (o + ti0 * 8) * SLD + p, SLD, 1, S + (o + tj0 * 8) * SLD + p, 1, SLD, 0, 8, -1.0, true,
+                                 a1, true, b1);
+#pragma unroll
+                    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                        for (int rj = 0; rj < 2; ++rj)
+                            if (v[ri][rj])
+                                *reinterpret_cast<double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q) =
+                                    make_double2(c[ri][rj][0], c[ri][rj][1]);
+                }
             }
         } else {
             for (int t = 0; t < ntiles; ++t) warp_trailing_tile(S, p, t);
             __syncwarp();
             warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
         }
+        if (warp != 0) { GPB_POTRF_STAMP(3) }
         __syncthreads();
+        GPB_POTRF_STAMP(4)
     }
 }
 
@@ -207,30 +294,65 @@ __device__ __forceinline__ void block_trtri_lower_inplace(double* S, int np, dou
     for (int b = 8; b < np; b <<= 1) {
         const int npairs = (np + 2 * b - 1) / (2 * b);
         const int bt = b >> 3;  // tiles per block edge
-        // T_pr = L21 W11  (W11 lower: k >= column tile)
-        for (int t = warp; t < npairs * bt * bt; t += nwarps) {
-            const int pr = t / (bt * bt), rem = t - pr * bt * bt, ti = rem / bt, tj = rem - ti * bt;
-            const int r0 = pr * 2 * b;
-            if (r0 + b + ti * 8 >= np) continue;   // second block shorter than b (or absent)
-            const double* L21 = S + (r0 + b + ti * 8) * SLD + r0;
-            const double* W11 = S + r0 * SLD + r0;
-            double c0 = 0.0, c1 = 0.0;
-            warp_tile_mma(c0, c1, L21 + tj * 8, SLD, 1, W11 + (tj * 8) * SLD + tj * 8, SLD, 1, b - tj * 8, 1.0);
-            double* out = T + (pr * b + ti * 8 + g) * TLD + tj * 8 + 2 * q;
-            *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
+        if (bt == 1) {
+            // 8x8 blocks: one tile product per pair and phase
+            for (int pr = warp; pr < npairs; pr += nwarps) {
+                const int r0 = pr * 2 * b;
+                if (r0 + b >= np) continue;
+                double c0 = 0.0, c1 = 0.0;
+                warp_tile_mma(c0, c1, S + (r0 + b) * SLD + r0, SLD, 1, S + r0 * SLD + r0, SLD, 1, b, 1.0);
+                *reinterpret_cast<double2*>(T + (pr * b + g) * TLD + 2 * q) = make_double2(c0, c1);
+            }
+            __syncthreads();
+            for (int pr = warp; pr < npairs; pr += nwarps) {
+                const int r0 = pr * 2 * b;
+                if (r0 + b >= np) continue;
+                double c0 = 0.0, c1 = 0.0;
+                warp_tile_mma(c0, c1, S + (r0 + b) * SLD + r0 + b, SLD, 1, T + (pr * b) * TLD, TLD, 1, b, -1.0);
+                *reinterpret_cast<double2*>(S + (r0 + b + g) * SLD + r0 + 2 * q) = make_double2(c0, c1);
+            }
+            __syncthreads();
+            continue;
+        }
+        const int hb = bt >> 1, nsup = npairs * hb * hb;   // 16x16 super-tiles per phase
+        // T_pr = L21 W11  (W11 lower: column tile tj needs k >= 8 tj only; its upper tiles hold garbage)
+        for (int t = warp; t < nsup; t += nwarps) {
+            const int pr = t / (hb * hb), rem = t - pr * hb * hb, I = rem / hb, J = rem - I * hb;
+            const int r0 = pr * 2 * b, ti0 = 2 * I, tj0 = 2 * J;
+            if (r0 + b + ti0 * 8 >= np) continue;                 // second block shorter than b (or absent)
+            const bool a1 = r0 + b + (ti0 + 1) * 8 < np;
+            double c[2][2][2] = {};
+            const double* L21 = S + (r0 + b + ti0 * 8) * SLD + r0;
+            const double* W11 = S + r0 * SLD + r0 + tj0 * 8;
+            warp_mma_2x2(c, L21, SLD, 1, W11, SLD, 1, tj0 * 8, tj0 * 8 + 8, 1.0, true, a1, true, false);
+            warp_mma_2x2(c, L21, SLD, 1, W11, SLD, 1, tj0 * 8 + 8, b, 1.0, true, a1, true, true);
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                for (int rj = 0; rj < 2; ++rj)
+                    if (ri == 0 || a1)
+                        *reinterpret_cast<double2*>(T + (pr * b + (ti0 + ri) * 8 + g) * TLD + (tj0 + rj) * 8 + 2 * q) =
+                            make_double2(c[ri][rj][0], c[ri][rj][1]);
         }
         __syncthreads();
-        // W21 = -W22 T  (W22 lower: k <= row tile)
-        for (int t = warp; t < npairs * bt * bt; t += nwarps) {
-            const int pr = t / (bt * bt), rem = t - pr * bt * bt, ti = rem / bt, tj = rem - ti * bt;
-            const int r0 = pr * 2 * b;
-            if (r0 + b + ti * 8 >= np) continue;
-            const double* W22 = S + (r0 + b + ti * 8) * SLD + r0 + b;
-            const double* Tp = T + (pr * b) * TLD + tj * 8;
-            double c0 = 0.0, c1 = 0.0;
-            warp_tile_mma(c0, c1, W22, SLD, 1, Tp, TLD, 1, (ti + 1) * 8, -1.0);
-            double* out = S + (r0 + b + ti * 8 + g) * SLD + r0 + tj * 8 + 2 * q;
-            *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
+        // W21 = -W22 T  (W22 lower: row tile ti needs k < 8 (ti + 1) only)
+        for (int t = warp; t < nsup; t += nwarps) {
+            const int pr = t / (hb * hb), rem = t - pr * hb * hb, I = rem / hb, J = rem - I * hb;
+            const int r0 = pr * 2 * b, ti0 = 2 * I, tj0 = 2 * J;
+            if (r0 + b + ti0 * 8 >= np) continue;
+            const bool a1 = r0 + b + (ti0 + 1) * 8 < np;
+            double c[2][2][2] = {};
+            const double* W22 = S + (r0 + b + ti0 * 8) * SLD + r0 + b;
+            const double* Tp = T + (pr * b) * TLD + tj0 * 8;
+            warp_mma_2x2(c, W22, SLD, 1, Tp, TLD, 1, 0, (ti0 + 1) * 8, -1.0, true, a1, true, true);
+            warp_mma_2x2(c, W22, SLD, 1, Tp, TLD, 1, (ti0 + 1) * 8, (ti0 + 2) * 8, -1.0, false, a1, true, true);
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                for (int rj = 0; rj < 2; ++rj)
+                    if (ri == 0 || a1)
+                        *reinterpret_cast<double2*>(S + (r0 + b + (ti0 + ri) * 8 + g) * SLD + r0 + (tj0 + rj) * 8 + 2 * q) =
+                            make_double2(c[ri][rj][0], c[ri][rj][1]);
         }
         __syncthreads();
     }

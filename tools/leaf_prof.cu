@@ -3,6 +3,11 @@
 #include <cstdio>
 #include <vector>
 #include <cmath>
+// per-warp phase accumulators of block_potrf_lower: [warp][0..4] = loop head, panel tile(s), barrier /
+// tile-0 update, trailing update / diagonal factor, end-of-step sync wait
+__shared__ long long prof_acc[16][5];
+#define GPB_POTRF_DECL long long t_last_ = clock64();
+#define GPB_POTRF_STAMP(i) { if ((threadIdx.x & 31) == 0) { const long long t_now_ = clock64(); prof_acc[threadIdx.x >> 5][i] += t_now_ - t_last_; t_last_ = t_now_; } }
 #include "../portfoliooptgp_b200/csrc/block_chol.cuh"
 using namespace gpb;
 namespace gpb {
@@ -126,10 +131,12 @@ __global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
     for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) S[i * SLD + j] = (j <= i) ? A[i * n + j] : 0.0; }
+    if (tid < 80) (&prof_acc[0][0])[tid] = 0;
     __syncthreads();
     long long t0 = clock64();
     block_potrf_lower(S, n, fail, dinv);
     long long t1 = clock64();
+    if (tid < 10) stamps[8 + tid] = prof_acc[tid / 5][tid % 5];          // warps 0 and 1
     block_trtri_lower_inplace(S, n, T, dinv);
     __syncthreads();
     long long t2 = clock64();
@@ -203,6 +210,9 @@ int main() {
         long long st[6]; cudaMemcpy(st, dS, 48, cudaMemcpyDeviceToHost);
         printf("current, threads %d cycles: potrf %lld trtri %lld | 16 diag factors %lld, panel product(p=0) %lld, trailing(p=0) %lld, syncthreads %lld (err %s)\n",
                threads, st[0], st[1], st[2], st[3], st[4], st[5], cudaGetErrorString(cudaGetLastError()));
+        long long pa[10]; cudaMemcpy(pa, dS + 8, 80, cudaMemcpyDeviceToHost);
+        printf("  potrf phases, warp 0: head %lld panel0 %lld tile0-update %lld diag %lld sync-wait %lld | warp 1: head %lld panel %lld barrier %lld trailing %lld sync-wait %lld\n",
+               pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], pa[6], pa[7], pa[8], pa[9]);
     }
     lat_kernel<<<1, 32>>>(dS, 1.3);
     long long l[7]; cudaMemcpy(l, dS, 56, cudaMemcpyDeviceToHost);
