@@ -101,7 +101,9 @@ int64_t gpb_launch_count(gpb_handle* h);
 
 /* Engine options.  option 0: fork off-critical-path products of the blocked factorisation onto side
  * streams (default 1; bench.py switches it off while it times individual kernels).  option 1: launch
- * the GEMM / leaf kernels with programmatic dependent launch (default 1). */
+ * the GEMM / leaf kernels with programmatic dependent launch (default 1).  option 2: use the
+ * straight-line instantiations of the element kernels for the known expression shapes
+ * (csrc/shapes.cuh; default 1, 0 forces the run-time interpreter -- same results). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 
 /* Optional kernel timing with CUDA events recorded on the handle's stream around each engine

@@ -170,6 +170,7 @@ class Engine:
 
     OPTION_FORK_STREAMS = 0
     OPTION_PDL = 1
+    OPTION_STATIC_SHAPES = 2
 
     def set_option(self, option: int, value: int):
         self._check(self._lib.gpb_set_option(self._h, int(option), int(value)), "gpb_set_option")

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "engine.cuh"
+#include "shapes.cuh"
 
 namespace gpb {
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ void tri_tile_index(int64_t b, int& ti, int& tj) {
 }
 
 // mode 0: full cross K(X, X2); 1: lower tiles of K(X, X) (+diag_add); 2: lower tiles + mirrored copy.
-template <int DP>
+template <int DP, class SH = DynShape>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
                 const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
@@ -74,7 +75,7 @@ assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__
     const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(Kout) & 15) == 0);
     const bool diag_tile = (mode != 0) && (ti == tj);
 
-    const bool fastk = (kp.n_leaves <= GRAD_FAST_LEAVES);
+    const bool fastk = SH::is_static || (kp.n_leaves <= GRAD_FAST_LEAVES);
 #pragma unroll 1
     for (int rr = 0; rr < ROWS_PT; rr += 2) {
         const int r = ty * ROWS_PT + rr;
@@ -86,7 +87,7 @@ assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__
         }
         double v[4];   // (r, c0) (r, c0+1) (r+1, c0) (r+1, c0+1)
         if (fastk) {
-            kernel_value_2x2<DP>(kp, xa, xb, xj0, xj1, v);
+            kernel_value_2x2<DP, SH>(kp, xa, xb, xj0, xj1, v);
         } else {
             v[0] = kernel_value<DP>(kp, xa, xj0);
             v[1] = kernel_value<DP>(kp, xa, xj1);
@@ -163,11 +164,12 @@ struct GramSmem {
     static constexpr int TOTAL = STAGE + TILE * TILE;
 };
 
-template <int DP>
+template <int DP, class SH = DynShape>
 __global__ void __launch_bounds__(ASM_THREADS, 2)
 assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
                      const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
-                     double diag_add, int tiles_n, int has_kink) {
+                     double diag_add, int tiles_n, int has_kink_rt) {
+    const int has_kink = SH::is_static ? SH::HAS_KINK : has_kink_rt;
     using L = GramSmem<DP>;
     constexpr int DPP = L::DPP;
     extern __shared__ __align__(16) double gsm[];
@@ -187,7 +189,7 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     const int64_t row0 = (int64_t)ti * TILE, col0 = (int64_t)tj * TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int G = kp.n_groups;
+    const int G = SH::n_groups(kp);
 
     // stage sqrt(w)-scaled coordinates of both tile sides for every group
     for (int e = tid; e < GRAM_GROUPS * TILE * DP; e += ASM_THREADS) {
@@ -229,9 +231,11 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     // expression shape (uniform): a plain sum of leaves needs no products / selects
     bool pure_sum = true;
     double mult[GRAD_FAST_LEAVES] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = 0; t < kp.n_terms; ++t) {
-        if (kp.terms[t].n_factors != 1) pure_sum = false;
-        const int id = kp.terms[t].leaf[0];
+    constexpr int TU = SH::is_static ? 8 : 1;
+#pragma unroll TU
+    for (int t = 0; t < SH::n_terms(kp); ++t) {
+        if (SH::term_nf(kp, t) != 1) pure_sum = false;
+        const int id = SH::term_leaf(kp, t, 0);
 #pragma unroll
         for (int l = 0; l < GRAD_FAST_LEAVES; ++l) mult[l] += (id == l) ? 1.0 : 0.0;
     }
@@ -257,7 +261,7 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                 }
             }
             const double dots[4] = {d0, d1, d2, d3};
-            const bool euclid = (gg < G) && (kp.groups[gg].kind == GPB_GROUP_EUCLID);
+            const bool euclid = (gg < G) && (SH::group_kind(kp, gg) == GPB_GROUP_EUCLID);
             const double nar = na[gg * TILE + r];
             if (euclid) {
                 // r^2 = |x|^2 + |x'|^2 - 2 x.x' ; integer tests on the high words (FP64 compares are slow):
@@ -301,11 +305,12 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
             // K = sum_l mult_l * leaf_l : accumulate straight into the outputs, no per-leaf arrays, no selects
 #pragma unroll
             for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
-                if (l < kp.n_leaves) {
+                if (l < SH::n_leaves(kp)) {
                     const DevLeaf& lf = kp.leaves[l];
+                    const int lk = SH::leaf_kind(kp, l), air = SH::leaf_arg_is_r(kp, l);
                     double vl[4];
-                    if (lf.group == 0) leaf_value_vec<4>(lf, s[0], vl);
-                    else leaf_value_vec<4>(lf, s[1], vl);
+                    if (SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], vl);
+                    else leaf_value_vec_k<4>(lf, lk, air, s[1], vl);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) out[e] = fma(mult[l], vl[e], out[e]);
                 }
@@ -316,19 +321,20 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
             for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v[l][e] = 0.0;
-                if (l < kp.n_leaves) {
+                if (l < SH::n_leaves(kp)) {
                     const DevLeaf& lf = kp.leaves[l];
-                    if (lf.group == 0) leaf_value_vec<4>(lf, s[0], v[l]);
-                    else leaf_value_vec<4>(lf, s[1], v[l]);
+                    const int lk = SH::leaf_kind(kp, l), air = SH::leaf_arg_is_r(kp, l);
+                    if (SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], v[l]);
+                    else leaf_value_vec_k<4>(lf, lk, air, s[1], v[l]);
                 }
             }
-            for (int t = 0; t < kp.n_terms; ++t) {
-                const DevTerm& tm = kp.terms[t];
+#pragma unroll TU
+            for (int t = 0; t < SH::n_terms(kp); ++t) {
                 double prod[4] = {1.0, 1.0, 1.0, 1.0};
 #pragma unroll
                 for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-                    if (f < tm.n_factors) {
-                        const int id = tm.leaf[f];
+                    if (f < SH::term_nf(kp, t)) {
+                        const int id = SH::term_leaf(kp, t, f);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             double fv = v[0][e];
@@ -406,7 +412,7 @@ __global__ void kdiag_kernel(const __grid_constant__ DevKernel kp, const double*
 // partial[b][P] = sum over diagonal elements of (alpha_i^2 - Kinv_ii).   dK/dtheta is recomputed from
 // the X tiles and never written.  HBM bytes: one read of the lower triangle of
 // Kinv (8 N(N+1)/2).
-template <int DP, bool FAST>
+template <int DP, bool FAST, class SH = DynShape>
 __global__ void __launch_bounds__(ASM_THREADS, FAST ? 2 : 1)
 grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N, int D,
                    const double* __restrict__ Kinv, int64_t ldk, const double* __restrict__ alpha,
@@ -473,13 +479,13 @@ grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restric
         {
             double w = ai * al_j[c0] - k0;
             if (gj == gi) { tr += w; } else { w *= 2.0; }
-            if (fast) kernel_value_grad_fast<DP>(kp, xi, xj0, w, A);
+            if (fast) kernel_value_grad_fast<DP, SH>(kp, xi, xj0, w, A);
             else kernel_value_grad<DP>(kp, xi, xj0, w, acc);
         }
         if (gj + 1 <= gi) {
             double w = ai * al_j[c0 + 1] - k1;
             if (gj + 1 == gi) { tr += w; } else { w *= 2.0; }
-            if (fast) kernel_value_grad_fast<DP>(kp, xi, xj1, w, A);
+            if (fast) kernel_value_grad_fast<DP, SH>(kp, xi, xj1, w, A);
             else kernel_value_grad<DP>(kp, xi, xj1, w, acc);
         }
     }
@@ -487,7 +493,7 @@ grad_reduce_kernel(const __grid_constant__ DevKernel kp, const double* __restric
     if (fast) {
         for (int p = tx; p <= P; p += 32) red[ty][p] = 0.0;
         __syncwarp();
-        grad_flush(kp, A, red[ty]);
+        grad_flush<SH>(kp, A, red[ty]);
     } else {
         for (int p = 0; p < P; ++p) {
             double v = acc[p];
@@ -548,40 +554,41 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
         if (kp.groups[g].kind != GPB_GROUP_EUCLID && kp.groups[g].kind != GPB_GROUP_DOT) gram = false;
     for (int l = 0; l < kp.n_leaves; ++l)
         if (kp.leaves[l].kind == GPB_LEAF_MATERN12 || kp.leaves[l].kind == GPB_LEAF_EXPONENTIAL) has_kink = 1;
+    const int shape = h->use_shapes ? match_shape(kp) : SHAPE_NONE;
     if (gram) {
         cudaError_t e = cudaSuccess;
-        switch (pad_dims(D)) {
-            case 4: {
-                static bool set4 = false;
-                constexpr int SM = GramSmem<4>::TOTAL * (int)sizeof(double);
-                if (!set4) { e = cudaFuncSetAttribute(assemble_gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set4 = true; }
-                if (e == cudaSuccess)
-                    assemble_gram_kernel<4><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
-                                                                                          diag_add, tiles_n, has_kink);
-            } break;
-            case 8: {
-                static bool set8 = false;
-                constexpr int SM = GramSmem<8>::TOTAL * (int)sizeof(double);
-                if (!set8) { e = cudaFuncSetAttribute(assemble_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set8 = true; }
-                if (e == cudaSuccess)
-                    assemble_gram_kernel<8><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
-                                                                                          diag_add, tiles_n, has_kink);
-            } break;
-            default: {
-                static bool set16 = false;
-                constexpr int SM = GramSmem<16>::TOTAL * (int)sizeof(double);
-                if (!set16) { e = cudaFuncSetAttribute(assemble_gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); set16 = true; }
-                if (e == cudaSuccess)
-                    assemble_gram_kernel<16><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(kp, d_X, N, d_X2, N2, D, d_K, ldk, mode,
-                                                                                           diag_add, tiles_n, has_kink);
-            } break;
-        }
+        // one attribute call per instantiation (static flag inside the macro body's scope)
+#define GPB_GRAM_LAUNCH(DPV)                                                                                            \
+    {                                                                                                                    \
+        static bool attr_set = false;                                                                                    \
+        constexpr int SM = GramSmem<DPV>::TOTAL * (int)sizeof(double);                                                   \
+        if (!attr_set) {                                                                                                 \
+            e = cudaFuncSetAttribute(assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)>,                                         \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM);                                   \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        if (e == cudaSuccess)                                                                                            \
+            assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(                  \
+                kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n, has_kink);                                   \
+    }
+#define GPB_SHAPE_BODY_                                  \
+    switch (pad_dims(D)) {                               \
+        case 4: GPB_GRAM_LAUNCH(4) break;                \
+        case 8: GPB_GRAM_LAUNCH(8) break;                \
+        default: GPB_GRAM_LAUNCH(16) break;              \
+    }
+        GPB_DISPATCH_SHAPE(shape)
+#undef GPB_SHAPE_BODY_
+#undef GPB_GRAM_LAUNCH
         if (e != cudaSuccess) return check_cuda(h, e, "assemble_gram cudaFuncSetAttribute");
         h->launches += 1;
         return check_cuda(h, cudaGetLastError(), "assemble_gram_kernel launch");
     }
-    GPB_DISPATCH_DP(D, (assemble_kernel<DP><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(
+#define GPB_SHAPE_BODY_                                                                                      \
+    GPB_DISPATCH_DP(D, (assemble_kernel<DP, GPB_SH_FOR(DP)><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(  \
                            kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n)));
+    GPB_DISPATCH_SHAPE(shape)
+#undef GPB_SHAPE_BODY_
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "assemble_kernel launch");
 }
@@ -602,9 +609,14 @@ int launch_grad_reduce(gpb_handle* h, const DevKernel& kp, const double* d_X, in
     double* partial = workspace(h, BUF_RED, (size_t)nblk * (GPB_MAX_PARAMS + 1) * sizeof(double));
     if (!partial) return -1;
     ProfScope prof(h, PROF_GRAD, h->stream);
+    const int shape = h->use_shapes ? match_shape(kp) : SHAPE_NONE;
     if (kp.n_leaves <= GRAD_FAST_LEAVES && !kp.has_ard) {
-        GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP, true><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv,
-                                                                                                        ldk, d_alpha, partial)));
+#define GPB_SHAPE_BODY_                                                                                                     \
+    GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP, true, GPB_SH_FOR(DP)><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, \
+                                                                                                         d_Kinv, ldk,     \
+                                                                                                         d_alpha, partial)));
+        GPB_DISPATCH_SHAPE(shape)
+#undef GPB_SHAPE_BODY_
     } else {
         GPB_DISPATCH_DP(D, (grad_reduce_kernel<DP, false><<<(unsigned)nblk, ASM_THREADS, 0, h->stream>>>(kp, d_X, N, D, d_Kinv,
                                                                                                          ldk, d_alpha, partial)));

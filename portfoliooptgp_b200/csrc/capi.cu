@@ -217,6 +217,7 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
     switch (option) {
         case 0: h->fork_streams = (value != 0); return 0;
         case 1: h->use_pdl = (value != 0); return 0;
+        case 2: h->use_shapes = (value != 0); return 0;
         default: return set_error(h, -2, "unknown option %d", option);
     }
 }

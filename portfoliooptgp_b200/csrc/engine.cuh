@@ -20,6 +20,7 @@ struct gpb_handle {
     std::string err;
     bool fork_streams = true;   // gpb_set_option(h, 0, x)
     bool use_pdl = true;        // gpb_set_option(h, 1, x): programmatic dependent launch for dgemm / leaf
+    bool use_shapes = true;     // gpb_set_option(h, 2, x): straight-line kernels for the known expression shapes (shapes.cuh)
     int64_t launches = 0;
     int sm_count = 148;
 

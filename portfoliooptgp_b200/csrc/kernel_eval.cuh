@@ -119,6 +119,73 @@ struct DevKernel {
     DevTerm terms[GPB_MAX_TERMS];
 };
 
+// ---- expression-shape policies --------------------------------------------------------------------
+// The evaluation routines below read the STRUCTURE of the expression (how many groups / leaves /
+// terms, their kinds, which leaf sits in which term) through a policy class.  DynShape reads it from
+// the descriptor at run time (the general interpreter: uniform branches, selects).  StaticShape
+// carries it in template arguments, so that after unrolling every kind switch, leaf select and term
+// loop folds away and the kernel body is the straight-line arithmetic of that one expression; the
+// parameter VALUES (variances, lengthscale weights, active-dimension masks, theta indices) still
+// come from the descriptor.  shapes.cuh lists the shapes that are instantiated (the reference's
+// kernel list) and matches a descriptor against them.
+struct DynShape {
+    static constexpr bool is_static = false;
+    static constexpr int HAS_KINK = 0;   // unused: the interpreter gets it as a kernel argument
+    static __host__ __device__ __forceinline__ int n_groups(const DevKernel& kp) { return kp.n_groups; }
+    static __host__ __device__ __forceinline__ int group_kind(const DevKernel& kp, int g) { return kp.groups[g].kind; }
+    static __host__ __device__ __forceinline__ int n_leaves(const DevKernel& kp) { return kp.n_leaves; }
+    static __host__ __device__ __forceinline__ int leaf_kind(const DevKernel& kp, int l) { return kp.leaves[l].kind; }
+    static __host__ __device__ __forceinline__ int leaf_group(const DevKernel& kp, int l) { return kp.leaves[l].group; }
+    static __host__ __device__ __forceinline__ int leaf_arg_is_r(const DevKernel& kp, int l) { return kp.leaves[l].arg_is_r; }
+    static __host__ __device__ __forceinline__ int n_terms(const DevKernel& kp) { return kp.n_terms; }
+    static __host__ __device__ __forceinline__ int term_nf(const DevKernel& kp, int t) { return kp.terms[t].n_factors; }
+    static __host__ __device__ __forceinline__ int term_leaf(const DevKernel& kp, int t, int f) { return kp.terms[t].leaf[f]; }
+};
+
+// G* = group kind (-1: unused); L* = leaf kind | group << 4 (-1: unused);
+// T* = n_factors | leaf0 << 4 | leaf1 << 8 | leaf2 << 12 | leaf3 << 16 (0: unused).  At most 2 groups, 4
+// leaves (the register-resident gradient path), 4 terms.
+template <int G0, int G1, int L0, int L1, int L2, int L3, int T0, int T1, int T2, int T3>
+struct StaticShape {
+    static constexpr bool is_static = true;
+    static constexpr int NG = (G0 >= 0) + (G1 >= 0);
+    static constexpr int NL = (L0 >= 0) + (L1 >= 0) + (L2 >= 0) + (L3 >= 0);
+    static constexpr int NT = (T0 != 0) + (T1 != 0) + (T2 != 0) + (T3 != 0);
+    static __host__ __device__ constexpr int lcode(int l) { return l == 0 ? L0 : l == 1 ? L1 : l == 2 ? L2 : L3; }
+    static __host__ __device__ constexpr int tcode(int t) { return t == 0 ? T0 : t == 1 ? T1 : t == 2 ? T2 : T3; }
+    static __host__ __device__ constexpr int kink_of(int c) {   // leaf with a kink at r = 0 (Matern12 / Exponential)
+        return (c >= 0 && ((c & 15) == GPB_LEAF_MATERN12 || (c & 15) == GPB_LEAF_EXPONENTIAL)) ? 1 : 0;
+    }
+    static constexpr int HAS_KINK = kink_of(L0) | kink_of(L1) | kink_of(L2) | kink_of(L3);
+    static __host__ __device__ constexpr int n_groups(const DevKernel&) { return NG; }
+    static __host__ __device__ constexpr int group_kind(const DevKernel&, int g) { return g == 0 ? G0 : G1; }
+    static __host__ __device__ constexpr int n_leaves(const DevKernel&) { return NL; }
+    static __host__ __device__ constexpr int leaf_kind(const DevKernel&, int l) { return lcode(l) & 15; }
+    static __host__ __device__ constexpr int leaf_group(const DevKernel&, int l) { return (lcode(l) >> 4) & 15; }
+    static __host__ __device__ constexpr int leaf_arg_is_r(const DevKernel&, int l) {
+        return (((lcode(l) >> 4) & 15) == 0 ? G0 : G1) == GPB_GROUP_PERIODIC_ABS ? 1 : 0;
+    }
+    static __host__ __device__ constexpr int n_terms(const DevKernel&) { return NT; }
+    static __host__ __device__ constexpr int term_nf(const DevKernel&, int t) { return tcode(t) & 15; }
+    static __host__ __device__ constexpr int term_leaf(const DevKernel&, int t, int f) { return (tcode(t) >> (4 + 4 * f)) & 15; }
+};
+
+// does the descriptor have exactly the structure SH encodes (and no per-dimension lengthscales)?
+template <class SH>
+inline bool shape_matches(const DevKernel& kp) {
+    if (kp.has_ard || kp.n_groups != SH::NG || kp.n_leaves != SH::NL || kp.n_terms != SH::NT) return false;
+    for (int g = 0; g < SH::NG; ++g)
+        if (kp.groups[g].kind != SH::group_kind(kp, g)) return false;
+    for (int l = 0; l < SH::NL; ++l)
+        if (kp.leaves[l].kind != SH::leaf_kind(kp, l) || kp.leaves[l].group != SH::leaf_group(kp, l)) return false;
+    for (int t = 0; t < SH::NT; ++t) {
+        if (kp.terms[t].n_factors != SH::term_nf(kp, t)) return false;
+        for (int f = 0; f < kp.terms[t].n_factors; ++f)
+            if (kp.terms[t].leaf[f] != SH::term_leaf(kp, t, f)) return false;
+    }
+    return true;
+}
+
 // ---- spec + theta -> DevKernel (host and device: the batched path builds one per GP in shared memory) --
 // Returns 0, or 1 + the theta index of a non-positive lengthscale.
 __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, const double* theta, DevKernel* out) {
@@ -177,11 +244,11 @@ __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, c
 // ---- group value -------------------------------------------------------------------------------
 // s = reduction over active dims; when GRAD also returns ds/dperiod.
 template <int DP, bool GRAD>
-__device__ __forceinline__ double group_value(const DevGroup& g, const double (&xi)[DP], const double (&xj)[DP],
-                                              double& ds_dperiod) {
+__device__ __forceinline__ double group_value_k(const DevGroup& g, int kind, const double (&xi)[DP],
+                                                const double (&xj)[DP], double& ds_dperiod) {
     double s = 0.0;
     if (GRAD) ds_dperiod = 0.0;
-    switch (g.kind) {
+    switch (kind) {
         case GPB_GROUP_EUCLID: {
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
@@ -225,6 +292,12 @@ __device__ __forceinline__ double group_value(const DevGroup& g, const double (&
     return s;
 }
 
+template <int DP, bool GRAD>
+__device__ __forceinline__ double group_value(const DevGroup& g, const double (&xi)[DP], const double (&xj)[DP],
+                                              double& ds_dperiod) {
+    return group_value_k<DP, GRAD>(g, g.kind, xi, xj, ds_dperiod);
+}
+
 // ---- leaf value ----------------------------------------------------------------------------------
 // v = variance * f(u), u = s * scale.  Returns v; when GRAD also
 //   f_out      = f(u)                       (dv/dvariance)
@@ -238,12 +311,12 @@ struct LeafOut {
 };
 
 template <bool GRAD>
-__device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
+__device__ __forceinline__ LeafOut leaf_value_k(const DevLeaf& lf, const int kind, const int arg_is_r, double s) {
     LeafOut o;
     o.dv_dalpha = 0.0;
     const double u = s * lf.scale;
     double f, fp_u, fp;  // f(u), f'(u)*u, f'(u)
-    switch (lf.kind) {
+    switch (kind) {
         case GPB_LEAF_LINEAR: {
             f = u; fp_u = u; fp = 1.0;
         } break;
@@ -261,13 +334,13 @@ __device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
         default: {
             // Matern family: needs r.  From an r^2 argument: r = sqrt(max(r2, 1e-36)) (GPflow K_r2);
             // from a PERIODIC_ABS group the argument already is r (GPflow calls K_r directly).
-            const double r = lf.arg_is_r ? u : sqrt(fmax(u, 1e-36));
+            const double r = arg_is_r ? u : sqrt(fmax(u, 1e-36));
             double df_dr;  // f'(r)
-            if (lf.kind == GPB_LEAF_MATERN12) {
+            if (kind == GPB_LEAF_MATERN12) {
                 f = gpb_exp(-r); df_dr = -f;
-            } else if (lf.kind == GPB_LEAF_EXPONENTIAL) {
+            } else if (kind == GPB_LEAF_EXPONENTIAL) {
                 f = gpb_exp(-0.5 * r); df_dr = -0.5 * f;
-            } else if (lf.kind == GPB_LEAF_MATERN32) {
+            } else if (kind == GPB_LEAF_MATERN32) {
                 const double s3 = 1.7320508075688772;
                 const double e = gpb_exp(-s3 * r);
                 f = (1.0 + s3 * r) * e; df_dr = -3.0 * r * e;
@@ -277,7 +350,7 @@ __device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
                 f = (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
                 df_dr = -(5.0 / 3.0) * r * (1.0 + s5 * r) * e;
             }
-            if (lf.arg_is_r) {
+            if (arg_is_r) {
                 fp = df_dr; fp_u = df_dr * r;
             } else {
                 // d/du = df/dr / (2 r); times u = r^2 -> df/dr * r / 2
@@ -294,6 +367,11 @@ __device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
         o.dv_ds = lf.variance * fp * lf.scale;
     }
     return o;
+}
+
+template <bool GRAD>
+__device__ __forceinline__ LeafOut leaf_value(const DevLeaf& lf, double s) {
+    return leaf_value_k<GRAD>(lf, lf.kind, lf.arg_is_r, s);
 }
 
 // ---- forward only: k(x, x') ----------------------------------------------------------------------
@@ -413,7 +491,7 @@ __device__ __forceinline__ double sel4(const double (&a)[GRAD_FAST_LEAVES], int 
 // Forward value with the leaves statically unrolled (same structure as the gradient fast path): the
 // per-leaf constants sit at compile-time offsets of the kernel-parameter block, so the compiler
 // hoists them out of the element loops instead of chasing term -> leaf -> group indices per element.
-template <int DP>
+template <int DP, class SH = DynShape>
 __device__ __forceinline__ double kernel_value_fast(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP]) {
     double v[GRAD_FAST_LEAVES];
     double s_prev = 0.0;
@@ -421,23 +499,25 @@ __device__ __forceinline__ double kernel_value_fast(const DevKernel& kp, const d
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
         v[l] = 0.0;
-        if (l < kp.n_leaves) {
+        if (l < SH::n_leaves(kp)) {
             const DevLeaf& lf = kp.leaves[l];
-            if (lf.group != g_prev) {
+            const int gi = SH::leaf_group(kp, l);
+            if (gi != g_prev) {
                 double dummy;
-                s_prev = group_value<DP, false>(kp.groups[lf.group], xi, xj, dummy);
-                g_prev = lf.group;
+                s_prev = group_value_k<DP, false>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dummy);
+                g_prev = gi;
             }
-            v[l] = leaf_value<false>(lf, s_prev).v;
+            v[l] = leaf_value_k<false>(lf, SH::leaf_kind(kp, l), SH::leaf_arg_is_r(kp, l), s_prev).v;
         }
     }
     double total = 0.0;
-    for (int t = 0; t < kp.n_terms; ++t) {
-        const DevTerm& tm = kp.terms[t];
-        double prod = sel4(v, tm.leaf[0]);
+    constexpr int TU = SH::is_static ? 8 : 1;
+#pragma unroll TU
+    for (int t = 0; t < SH::n_terms(kp); ++t) {
+        double prod = sel4(v, SH::term_leaf(kp, t, 0));
 #pragma unroll
         for (int f = 1; f < GPB_MAX_FACTORS; ++f)
-            if (f < tm.n_factors) prod *= sel4(v, tm.leaf[f]);
+            if (f < SH::term_nf(kp, t)) prod *= sel4(v, SH::term_leaf(kp, t, f));
         total += prod;
     }
     return total;
@@ -446,9 +526,10 @@ __device__ __forceinline__ double kernel_value_fast(const DevKernel& kp, const d
 // Vectorised leaf: v[e] = variance * f(s[e] * scale) for V elements at once (uniform switch outside,
 // the exponentials of all V elements share the coefficient loads through exp_vec).
 template <int V>
-__device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (&s)[V], double (&v)[V]) {
+__device__ __forceinline__ void leaf_value_vec_k(const DevLeaf& lf, const int kind, const int arg_is_r, const double (&s)[V],
+                                                 double (&v)[V]) {
     double a[V];
-    switch (lf.kind) {
+    switch (kind) {
         case GPB_LEAF_LINEAR: {
 #pragma unroll
             for (int e = 0; e < V; ++e) v[e] = lf.variance * (s[e] * lf.scale);
@@ -462,35 +543,40 @@ __device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (
         } break;
         case GPB_LEAF_RQ: {
 #pragma unroll
-            for (int e = 0; e < V; ++e) v[e] = leaf_value<false>(lf, s[e]).v;
+            for (int e = 0; e < V; ++e) v[e] = leaf_value_k<false>(lf, kind, arg_is_r, s[e]).v;
         } break;
         default: {
             double r[V];
-            const double c = (lf.kind == GPB_LEAF_MATERN12) ? 1.0
-                             : (lf.kind == GPB_LEAF_EXPONENTIAL) ? 0.5
-                             : (lf.kind == GPB_LEAF_MATERN32) ? 1.7320508075688772 : 2.23606797749979;
+            const double c = (kind == GPB_LEAF_MATERN12) ? 1.0
+                             : (kind == GPB_LEAF_EXPONENTIAL) ? 0.5
+                             : (kind == GPB_LEAF_MATERN32) ? 1.7320508075688772 : 2.23606797749979;
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const double u = s[e] * lf.scale;
                 // sqrt(max(u, 1e-36)) with an integer test on the high word (u >= 0 here): hi(1e-36) = 0x38754484
-                r[e] = lf.arg_is_r ? u : ((__double2hiint(u) < 0x38754484) ? 1e-18 : sqrt(u));
+                r[e] = arg_is_r ? u : ((__double2hiint(u) < 0x38754484) ? 1e-18 : sqrt(u));
                 a[e] = -c * r[e];
             }
             exp_vec<V>(a);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 double poly = 1.0;
-                if (lf.kind == GPB_LEAF_MATERN32) poly = 1.0 + c * r[e];
-                else if (lf.kind == GPB_LEAF_MATERN52) poly = 1.0 + c * r[e] + (5.0 / 3.0) * r[e] * r[e];
+                if (kind == GPB_LEAF_MATERN32) poly = 1.0 + c * r[e];
+                else if (kind == GPB_LEAF_MATERN52) poly = 1.0 + c * r[e] + (5.0 / 3.0) * r[e] * r[e];
                 v[e] = lf.variance * (poly * a[e]);
             }
         } break;
     }
 }
 
+template <int V>
+__device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (&s)[V], double (&v)[V]) {
+    leaf_value_vec_k<V>(lf, lf.kind, lf.arg_is_r, s, v);
+}
+
 // k for the 2 x 2 block {xa, xb} x {xj0, xj1}: out = {k(xa,xj0), k(xa,xj1), k(xb,xj0), k(xb,xj1)}.
 // Same arithmetic per element as kernel_value_fast; four elements advance together.
-template <int DP>
+template <int DP, class SH = DynShape>
 __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const double (&xa)[DP], const double (&xb)[DP],
                                                  const double (&xj0)[DP], const double (&xj1)[DP], double (&out)[4]) {
     double v[GRAD_FAST_LEAVES][4];
@@ -500,31 +586,34 @@ __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const doub
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[l][e] = 0.0;
-        if (l < kp.n_leaves) {
+        if (l < SH::n_leaves(kp)) {
             const DevLeaf& lf = kp.leaves[l];
-            if (lf.group != g_prev) {
+            const int gi = SH::leaf_group(kp, l);
+            if (gi != g_prev) {
                 double dummy;
-                const DevGroup& g = kp.groups[lf.group];
-                s[0] = group_value<DP, false>(g, xa, xj0, dummy);
-                s[1] = group_value<DP, false>(g, xa, xj1, dummy);
-                s[2] = group_value<DP, false>(g, xb, xj0, dummy);
-                s[3] = group_value<DP, false>(g, xb, xj1, dummy);
-                g_prev = lf.group;
+                const DevGroup& g = kp.groups[gi];
+                const int gk = SH::group_kind(kp, gi);
+                s[0] = group_value_k<DP, false>(g, gk, xa, xj0, dummy);
+                s[1] = group_value_k<DP, false>(g, gk, xa, xj1, dummy);
+                s[2] = group_value_k<DP, false>(g, gk, xb, xj0, dummy);
+                s[3] = group_value_k<DP, false>(g, gk, xb, xj1, dummy);
+                g_prev = gi;
             }
-            leaf_value_vec<4>(lf, s, v[l]);
+            leaf_value_vec_k<4>(lf, SH::leaf_kind(kp, l), SH::leaf_arg_is_r(kp, l), s, v[l]);
         }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) out[e] = 0.0;
-    for (int t = 0; t < kp.n_terms; ++t) {
-        const DevTerm& tm = kp.terms[t];
+    constexpr int TU = SH::is_static ? 8 : 1;
+#pragma unroll TU
+    for (int t = 0; t < SH::n_terms(kp); ++t) {
         double prod[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) prod[e] = 1.0;
 #pragma unroll
         for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-            if (f < tm.n_factors) {
-                const int id = tm.leaf[f];
+            if (f < SH::term_nf(kp, t)) {
+                const int id = SH::term_leaf(kp, t, f);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     double fv = v[0][e];
@@ -539,7 +628,7 @@ __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const doub
     }
 }
 
-template <int DP>
+template <int DP, class SH = DynShape>
 __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, const double (&xi)[DP],
                                                          const double (&xj)[DP], double wgt, GradAcc& A) {
     double v[GRAD_FAST_LEAVES], fval[GRAD_FAST_LEAVES], dls[GRAD_FAST_LEAVES], dal[GRAD_FAST_LEAVES],
@@ -549,25 +638,28 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
         v[l] = 1.0; fval[l] = dls[l] = dal[l] = dper[l] = 0.0; ladj[l] = 0.0;
-        if (l < kp.n_leaves) {
+        if (l < SH::n_leaves(kp)) {
             const DevLeaf& lf = kp.leaves[l];
-            if (lf.group != g_prev) {
-                s_prev = group_value<DP, true>(kp.groups[lf.group], xi, xj, dsp_prev);
-                g_prev = lf.group;
+            const int gi = SH::leaf_group(kp, l), air = SH::leaf_arg_is_r(kp, l);
+            if (gi != g_prev) {
+                s_prev = group_value_k<DP, true>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
+                g_prev = gi;
             }
-            const LeafOut lo = leaf_value<true>(lf, s_prev);
+            const LeafOut lo = leaf_value_k<true>(lf, SH::leaf_kind(kp, l), air, s_prev);
             v[l] = lo.v;
             fval[l] = lo.f;
-            dls[l] = lo.dv_du_u * (lf.arg_is_r ? -1.0 : -2.0) * lf.inv_ls;   // inv_ls = 0 without a scalar lengthscale
+            dls[l] = lo.dv_du_u * (air ? -1.0 : -2.0) * lf.inv_ls;   // inv_ls = 0 without a scalar lengthscale
             dal[l] = lo.dv_dalpha;
-            dper[l] = lo.dv_ds * dsp_prev;                                   // 0 for non-periodic groups
+            dper[l] = lo.dv_ds * dsp_prev;                            // 0 for non-periodic groups
         }
     }
     double total = 0.0;
-    for (int t = 0; t < kp.n_terms; ++t) {
-        const DevTerm& tm = kp.terms[t];
-        if (tm.n_factors == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
-            const int id = tm.leaf[0];
+    constexpr int TU = SH::is_static ? 8 : 1;
+#pragma unroll TU
+    for (int t = 0; t < SH::n_terms(kp); ++t) {
+        const int nf = SH::term_nf(kp, t);
+        if (nf == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
+            const int id = SH::term_leaf(kp, t, 0);
             total += sel4(v, id);
 #pragma unroll
             for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? wgt : 0.0;
@@ -577,18 +669,18 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
         double prod = 1.0;
 #pragma unroll
         for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-            fv[f] = (f < tm.n_factors) ? sel4(v, tm.leaf[f]) : 1.0;
+            fv[f] = (f < nf) ? sel4(v, SH::term_leaf(kp, t, f)) : 1.0;
             prod *= fv[f];
         }
         total += prod;
 #pragma unroll
         for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-            if (f < tm.n_factors) {
+            if (f < nf) {
                 double adj = wgt;
 #pragma unroll
                 for (int f2 = 0; f2 < GPB_MAX_FACTORS; ++f2)
-                    if (f2 != f) adj *= fv[f2];
-                const int id = tm.leaf[f];
+                    if (f2 != f && f2 < nf) adj *= fv[f2];
+                const int id = SH::term_leaf(kp, t, f);
 #pragma unroll
                 for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? adj : 0.0;
             }
@@ -596,19 +688,31 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
     }
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
-        A.var[l] = fma(ladj[l], fval[l], A.var[l]);
-        A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
-        A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
-        A.period[l] = fma(ladj[l], dper[l], A.period[l]);
+        if (SH::is_static) {
+            // only the slots this expression has: a leaf beyond n_leaves, a Linear leaf's lengthscale,
+            // a non-RQ alpha and a non-periodic period never receive anything
+            if (l < SH::n_leaves(kp)) {
+                const int lk = SH::leaf_kind(kp, l), gk = SH::group_kind(kp, SH::leaf_group(kp, l));
+                A.var[l] = fma(ladj[l], fval[l], A.var[l]);
+                if (lk != GPB_LEAF_LINEAR) A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
+                if (lk == GPB_LEAF_RQ) A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
+                if (gk == GPB_GROUP_PERIODIC_SQ || gk == GPB_GROUP_PERIODIC_ABS) A.period[l] = fma(ladj[l], dper[l], A.period[l]);
+            }
+        } else {
+            A.var[l] = fma(ladj[l], fval[l], A.var[l]);
+            A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
+            A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
+            A.period[l] = fma(ladj[l], dper[l], A.period[l]);
+        }
     }
     return total;
 }
 
 // gx[d] += coef * ds/dx_d for one group (derivative w.r.t. the FIRST argument x)
 template <int DP>
-__device__ __forceinline__ void add_group_dx(const DevGroup& g, const double (&xi)[DP], const double (&xj)[DP],
-                                             double coef, double (&gx)[DP]) {
-    switch (g.kind) {
+__device__ __forceinline__ void add_group_dx_k(const DevGroup& g, const int kind, const double (&xi)[DP],
+                                               const double (&xj)[DP], double coef, double (&gx)[DP]) {
+    switch (kind) {
         case GPB_GROUP_EUCLID: {
 #pragma unroll
             for (int d = 0; d < DP; ++d) gx[d] = fma(2.0 * coef * g.w[d], xi[d] - xj[d], gx[d]);
@@ -643,7 +747,7 @@ __device__ __forceinline__ void add_group_dx(const DevGroup& g, const double (&x
 
 // As kernel_value_grad_fast, and additionally gx[d] += wgt * dk(x, x')/dx_d (first argument): the
 // inducing-point gradient of the SVGP path (gpflow trains inducing_variable.Z).
-template <int DP>
+template <int DP, class SH = DynShape>
 __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, const double (&xi)[DP],
                                                            const double (&xj)[DP], double wgt, GradAcc& A,
                                                            double (&gx)[DP]) {
@@ -654,26 +758,29 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
         v[l] = 1.0; fval[l] = dls[l] = dal[l] = dper[l] = dvds[l] = 0.0; ladj[l] = 0.0;
-        if (l < kp.n_leaves) {
+        if (l < SH::n_leaves(kp)) {
             const DevLeaf& lf = kp.leaves[l];
-            if (lf.group != g_prev) {
-                s_prev = group_value<DP, true>(kp.groups[lf.group], xi, xj, dsp_prev);
-                g_prev = lf.group;
+            const int gi = SH::leaf_group(kp, l), air = SH::leaf_arg_is_r(kp, l);
+            if (gi != g_prev) {
+                s_prev = group_value_k<DP, true>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
+                g_prev = gi;
             }
-            const LeafOut lo = leaf_value<true>(lf, s_prev);
+            const LeafOut lo = leaf_value_k<true>(lf, SH::leaf_kind(kp, l), air, s_prev);
             v[l] = lo.v;
             fval[l] = lo.f;
-            dls[l] = lo.dv_du_u * (lf.arg_is_r ? -1.0 : -2.0) * lf.inv_ls;
+            dls[l] = lo.dv_du_u * (air ? -1.0 : -2.0) * lf.inv_ls;
             dal[l] = lo.dv_dalpha;
             dper[l] = lo.dv_ds * dsp_prev;
             dvds[l] = lo.dv_ds;
         }
     }
     double total = 0.0;
-    for (int t = 0; t < kp.n_terms; ++t) {
-        const DevTerm& tm = kp.terms[t];
-        if (tm.n_factors == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
-            const int id = tm.leaf[0];
+    constexpr int TU = SH::is_static ? 8 : 1;
+#pragma unroll TU
+    for (int t = 0; t < SH::n_terms(kp); ++t) {
+        const int nf = SH::term_nf(kp, t);
+        if (nf == 1) {   // plain summand (the common case): adjoint of the leaf is the weight
+            const int id = SH::term_leaf(kp, t, 0);
             total += sel4(v, id);
 #pragma unroll
             for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? wgt : 0.0;
@@ -683,18 +790,18 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
         double prod = 1.0;
 #pragma unroll
         for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-            fv[f] = (f < tm.n_factors) ? sel4(v, tm.leaf[f]) : 1.0;
+            fv[f] = (f < nf) ? sel4(v, SH::term_leaf(kp, t, f)) : 1.0;
             prod *= fv[f];
         }
         total += prod;
 #pragma unroll
         for (int f = 0; f < GPB_MAX_FACTORS; ++f) {
-            if (f < tm.n_factors) {
+            if (f < nf) {
                 double adj = wgt;
 #pragma unroll
                 for (int f2 = 0; f2 < GPB_MAX_FACTORS; ++f2)
-                    if (f2 != f) adj *= fv[f2];
-                const int id = tm.leaf[f];
+                    if (f2 != f && f2 < nf) adj *= fv[f2];
+                const int id = SH::term_leaf(kp, t, f);
 #pragma unroll
                 for (int l = 0; l < GRAD_FAST_LEAVES; ++l) ladj[l] += (id == l) ? adj : 0.0;
             }
@@ -703,15 +810,17 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
     double cacc = 0.0;
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        if (SH::is_static && l >= SH::n_leaves(kp)) continue;
         A.var[l] = fma(ladj[l], fval[l], A.var[l]);
         A.ls[l] = fma(ladj[l], dls[l], A.ls[l]);
         A.alpha[l] = fma(ladj[l], dal[l], A.alpha[l]);
         A.period[l] = fma(ladj[l], dper[l], A.period[l]);
-        if (l < kp.n_leaves) {
+        if (l < SH::n_leaves(kp)) {
             cacc = fma(ladj[l], dvds[l], cacc);
-            const bool last = (l + 1 >= kp.n_leaves) || (kp.leaves[l + 1].group != kp.leaves[l].group);
+            const int gi = SH::leaf_group(kp, l);
+            const bool last = (l + 1 >= SH::n_leaves(kp)) || (SH::leaf_group(kp, l + 1 < GRAD_FAST_LEAVES ? l + 1 : l) != gi);
             if (last) {
-                add_group_dx<DP>(kp.groups[kp.leaves[l].group], xi, xj, cacc, gx);
+                add_group_dx_k<DP>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, cacc, gx);
                 cacc = 0.0;
             }
         }
@@ -721,10 +830,12 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
 
 // Warp-reduce the register accumulators (fixed shuffle tree) and let lane 0 add them into out[0..P)
 // (a zero-initialised per-warp row, any memory space) at their theta indices, in a fixed order.
+template <class SH = DynShape>
 __device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, double* out) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {
+        if (SH::is_static && l >= SH::n_leaves(kp)) continue;
         double a = A.var[l], b = A.ls[l], c = A.alpha[l], d = A.period[l];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -733,7 +844,7 @@ __device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, doub
             c += __shfl_down_sync(0xffffffffu, c, o);
             d += __shfl_down_sync(0xffffffffu, d, o);
         }
-        if (lane == 0 && l < kp.n_leaves) {
+        if (lane == 0 && l < SH::n_leaves(kp)) {
             const DevLeaf& lf = kp.leaves[l];
             out[lf.var_index] += a;
             if (lf.ls_index >= 0) out[lf.ls_index] += b;
@@ -745,8 +856,9 @@ __device__ __forceinline__ void grad_flush(const DevKernel& kp, GradAcc& A, doub
 }
 
 // dispatch: statically unrolled path when the expression has <= GRAD_FAST_LEAVES leaves
-template <int DP>
+template <int DP, class SH = DynShape>
 __device__ __forceinline__ double kernel_value_auto(const DevKernel& kp, const double (&xi)[DP], const double (&xj)[DP]) {
+    if (SH::is_static) return kernel_value_fast<DP, SH>(kp, xi, xj);
     return (kp.n_leaves <= GRAD_FAST_LEAVES) ? kernel_value_fast<DP>(kp, xi, xj) : kernel_value<DP>(kp, xi, xj);
 }
 

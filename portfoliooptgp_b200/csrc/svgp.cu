@@ -25,6 +25,7 @@
 #include <math.h>
 
 #include "engine.cuh"
+#include "shapes.cuh"
 
 namespace gpb {
 
@@ -36,7 +37,7 @@ constexpr int CG_THREADS = 256;
 
 // theta_part[block][p] = sum over the block's tiles of Wt[i][j] dk(a_i, b_j)/dtheta_p
 // zbar_part[split][i][d] = zscale * sum_j Wt[i][j] dk(a_i, b_j)/da_i[d]
-template <int DP>
+template <int DP, class SH = DynShape>
 __global__ void __launch_bounds__(CG_THREADS)
 cross_grad_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ Arows, int Na,
                   const double* __restrict__ Bcols, int Nb, int D, const double* __restrict__ Wt, int64_t ldw,
@@ -82,7 +83,7 @@ cross_grad_kernel(const __grid_constant__ DevKernel kp, const double* __restrict
 #pragma unroll
                 for (int d = 0; d < DP; ++d) xj[d] = xb[cc][d];
                 const double w = wst[r * (CG_TILE + 1) + cc];
-                kernel_value_grad_x_fast<DP>(kp, xi, xj, w, A, gx);
+                kernel_value_grad_x_fast<DP, SH>(kp, xi, xj, w, A, gx);
             }
         }
     }
@@ -94,7 +95,7 @@ cross_grad_kernel(const __grid_constant__ DevKernel kp, const double* __restrict
     const int P = kp.n_params;
     for (int p = lane; p < P; p += 32) red[warp][p] = 0.0;
     __syncwarp();
-    grad_flush(kp, A, red[warp]);
+    grad_flush<SH>(kp, A, red[warp]);
     __syncthreads();
     for (int e = tid; e < CG_TILE * DP; e += CG_THREADS) {
         const int rr = e / DP, d = e % DP;
@@ -371,8 +372,12 @@ static int cross_grad(gpb_handle* h, const DevKernel& kp, const double* Arows, i
     double* zpart = part + tp;
     ProfScope prof(h, PROF_SVGP, h->stream);
     dim3 grid((unsigned)row_tiles, (unsigned)nsplit);
-    SVGP_DISPATCH_DP(D, (cross_grad_kernel<DP><<<grid, CG_THREADS, 0, h->stream>>>(kp, Arows, (int)Na, Bcols, (int)Nb, D, Wt,
-                                                                                    ldw, zscale, part, zpart)));
+    const int shape = h->use_shapes ? match_shape(kp) : SHAPE_NONE;
+#define GPB_SHAPE_BODY_                                                                                                  \
+    SVGP_DISPATCH_DP(D, (cross_grad_kernel<DP, GPB_SH_FOR(DP)><<<grid, CG_THREADS, 0, h->stream>>>(kp, Arows, (int)Na, Bcols, (int)Nb, \
+                                                                                        D, Wt, ldw, zscale, part, zpart)));
+    GPB_DISPATCH_SHAPE(shape)
+#undef GPB_SHAPE_BODY_
     int rc = check_cuda(h, cudaGetLastError(), "cross_grad_kernel launch");
     if (rc) return rc;
     reduce_rows_kernel<<<kp.n_params, 256, 0, h->stream>>>(part, (int64_t)row_tiles * nsplit, GPB_MAX_PARAMS, 1.0, g_theta,
