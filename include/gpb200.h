@@ -105,6 +105,9 @@ int64_t gpb_launch_count(gpb_handle* h);
  * straight-line instantiations of the element kernels for the known expression shapes
  * (csrc/shapes.cuh; default 1, 0 forces the run-time interpreter -- same results). */
 int gpb_set_option(gpb_handle* h, int option, int value);
+/* Diagnostics: which straight-line shape (csrc/shapes.cuh, 1-based id) the current expression matches;
+ * 0 = none, the run-time interpreter evaluates it (also when option 2 is off).  < 0: error. */
+int gpb_kernel_shape(gpb_handle* h);
 
 /* Optional kernel timing with CUDA events recorded on the handle's stream around each engine
  * launch, by category (0 DMMA GEMM, 1 assembly, 2 Cholesky leaf, 3 fused gradient reduction,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "gpb_last_error": (C.c_char_p, [_P]),
     "gpb_set_stream": (_INT, [_P, _P]),
     "gpb_launch_count": (_I64, [_P]),
+    "gpb_kernel_shape": (_INT, [_P]),
     "gpb_set_option": (_INT, [_P, _INT, _INT]),
     "gpb_profile_enable": (_INT, [_P, _INT]),
     "gpb_profile_read": (_INT, [_P, _DP, C.POINTER(C.c_int64)]),
@@ -162,6 +163,13 @@ class Engine:
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.gpb_set_stream(self._h, _P(cuda_stream)), "gpb_set_stream")
+
+    def kernel_shape(self) -> int:
+        """1-based id of the straight-line shape (csrc/shapes.cuh) the current expression matches; 0 = interpreter."""
+        rc = int(self._lib.gpb_kernel_shape(self._h))
+        if rc < 0:
+            self._check(rc, "gpb_kernel_shape")
+        return rc
 
     def launch_count(self) -> int:
         return int(self._lib.gpb_launch_count(self._h))

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "engine.cuh"
+#include "shapes.cuh"
 
 namespace gpb {
 
@@ -211,6 +212,17 @@ int gpb_set_stream(gpb_handle* h, void* cuda_stream) {
 }
 
 int64_t gpb_launch_count(gpb_handle* h) { return h ? h->launches : -1; }
+
+int gpb_kernel_shape(gpb_handle* h) {
+    if (!h) return -1;
+    if (!h->has_spec) return set_error(h, -3, "kernel_shape: no kernel set (gpb_set_kernel)");
+    if (!h->use_shapes) return 0;
+    double ones[GPB_MAX_PARAMS];
+    for (int p = 0; p < GPB_MAX_PARAMS; ++p) ones[p] = 1.0;
+    DevKernel probe;
+    build_dev_kernel_core(h->spec, ones, &probe);
+    return match_shape(probe);
+}
 
 int gpb_set_option(gpb_handle* h, int option, int value) {
     if (!h) return -1;
