@@ -153,24 +153,34 @@ assemble_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__
 // non-smooth Matern12 / Exponential leaves, r^2 < 1e-8 (|x|^2 + |x'|^2) (near-coincident points).
 constexpr int GRAM_GROUPS = 2;
 
-template <int DP>
+template <class SH>
+__host__ __device__ constexpr int gram_groups_of() {
+    if constexpr (SH::is_static) return SH::NG < 1 ? 1 : SH::NG;
+    else return GRAM_GROUPS;
+}
+
+template <int DP, int GG = GRAM_GROUPS>
 struct GramSmem {
     static constexpr int DPP = (DP % 8 == 0) ? DP + 4 : DP;   // row stride: conflict-free fragment loads
     static constexpr int A = 0;                                // [G][64][DPP] scaled rows
-    static constexpr int B = A + GRAM_GROUPS * TILE * DPP;      // [G][64][DPP] scaled cols
-    static constexpr int NA = B + GRAM_GROUPS * TILE * DPP;     // [G][64]
-    static constexpr int NB_ = NA + GRAM_GROUPS * TILE;         // [G][64]
-    static constexpr int STAGE = NB_ + GRAM_GROUPS * TILE;      // [64][64] mirror staging
+    static constexpr int B = A + GG * TILE * DPP;      // [G][64][DPP] scaled cols
+    static constexpr int NA = B + GG * TILE * DPP;     // [G][64]
+    static constexpr int NB_ = NA + GG * TILE;         // [G][64]
+    static constexpr int STAGE = NB_ + GG * TILE;      // [64][64] mirror staging
     static constexpr int TOTAL = STAGE + TILE * TILE;
 };
 
 template <int DP, class SH = DynShape>
-__global__ void __launch_bounds__(ASM_THREADS, 2)
+__global__ void __launch_bounds__(ASM_THREADS, 3)
 assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
                      const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
                      double diag_add, int tiles_n, int has_kink_rt) {
     const int has_kink = SH::is_static ? SH::HAS_KINK : has_kink_rt;
-    using L = GramSmem<DP>;
+    // distance groups held in shared memory / registers: exactly the shape's for a static shape.  The
+    // mirror staging tile exists only in mode 2 (the launch sizes the dynamic shared memory accordingly),
+    // so that lower / cross launches fit three CTAs per SM.
+    constexpr int GG = gram_groups_of<SH>();
+    using L = GramSmem<DP, GG>;
     constexpr int DPP = L::DPP;
     extern __shared__ __align__(16) double gsm[];
     double* As = gsm + L::A;
@@ -192,7 +202,7 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     const int G = SH::n_groups(kp);
 
     // stage sqrt(w)-scaled coordinates of both tile sides for every group
-    for (int e = tid; e < GRAM_GROUPS * TILE * DP; e += ASM_THREADS) {
+    for (int e = tid; e < GG * TILE * DP; e += ASM_THREADS) {
         const int gg = e / (TILE * DP), rem = e - gg * TILE * DP, r = rem / DP, d = rem - r * DP;
         double a = 0.0, b = 0.0;
         if (gg < G) {
@@ -204,8 +214,10 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
         As[(gg * TILE + r) * DPP + d] = a;
         Bs[(gg * TILE + r) * DPP + d] = b;
     }
+    __shared__ int nbmax_hi[1];
+    if (tid == 0) nbmax_hi[0] = 0;
     __syncthreads();
-    for (int e = tid; e < GRAM_GROUPS * TILE; e += ASM_THREADS) {
+    for (int e = tid; e < GG * TILE; e += ASM_THREADS) {
         double sa = 0.0, sb = 0.0;
 #pragma unroll
         for (int d = 0; d < DP; ++d) {
@@ -215,6 +227,7 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
         }
         na[e] = sa;
         nb[e] = sb;
+        atomicMax(nbmax_hi, __double2hiint(sb));   // norms are >= 0: their high words order like the values
     }
     __syncthreads();
 
@@ -222,9 +235,9 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     const bool diag_tile = (mode != 0) && (ti == tj);
     const int r = warp * 8 + g;               // tile row of this thread
     // A fragments of this warp's 8 rows, all groups, all k-steps (reused for the 8 column tiles)
-    double afr[GRAM_GROUPS][DP / 4];
+    double afr[GG][DP / 4];
 #pragma unroll
-    for (int gg = 0; gg < GRAM_GROUPS; ++gg)
+    for (int gg = 0; gg < GG; ++gg)
 #pragma unroll
         for (int ks = 0; ks < DP / 4; ++ks) afr[gg][ks] = As[(gg * TILE + r) * DPP + ks * 4 + q];
 
@@ -245,9 +258,9 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     for (int ct = 0; ct < TILE / 8; ct += 2) {
         // four elements of this thread: (r, c), (r, c + 1), (r, c + 8), (r, c + 9) with c = ct*8 + 2q
         const int c = ct * 8 + 2 * q;
-        double s[GRAM_GROUPS][4];
+        double s[GG][4];
 #pragma unroll
-        for (int gg = 0; gg < GRAM_GROUPS; ++gg) {
+        for (int gg = 0; gg < GG; ++gg) {
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
             if (gg < G) {
 #pragma unroll
@@ -263,6 +276,10 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
             const double dots[4] = {d0, d1, d2, d3};
             const bool euclid = (gg < G) && (SH::group_kind(kp, gg) == GPB_GROUP_EUCLID);
             const double nar = na[gg * TILE + r];
+            // |x|^2 + |x'|^2 <= |x_r|^2 + max_tile |x'|^2: when even that bound is below the cancellation
+            // threshold (standardised inputs: always) and the expression has no kink leaf, no element of
+            // this thread needs a guard and the per-element tests are skipped
+            const bool unguarded = !has_kink && (__double2hiint(nar + __hiloint2double(nbmax_hi[0] + 1, 0)) <= 0x40500000);
             if (euclid) {
                 // r^2 = |x|^2 + |x'|^2 - 2 x.x' ; integer tests on the high words (FP64 compares are slow):
                 //   negative -> 0 ; cancellation guard |x|^2+|x'|^2 > 64, or (kink kernels) r^2 < 2^-27 (...)
@@ -272,11 +289,12 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                 for (int e = 0; e < 4; ++e) {
                     const int cc = c + (e & 1) + ((e >> 1) << 3);
                     nn[e] = nar + nb[gg * TILE + cc];
-                    double val = fma(-2.0, dots[e], nn[e]);
-                    const int hv = __double2hiint(val), hn = __double2hiint(nn[e]);
-                    if (hv < 0) val = 0.0;
-                    guard |= (hn > 0x40500000) | (has_kink & (hv < hn - (27 << 20)));
-                    s[gg][e] = val;
+                    const double val = fma(-2.0, dots[e], nn[e]);   // may round to a tiny negative: harmless for
+                    s[gg][e] = val;                                  // SE / RQ, clamped inside the sqrt leaves
+                    if (!unguarded) {
+                        const int hv = __double2hiint(val), hn = __double2hiint(nn[e]);
+                        guard |= (hn > 0x40500000) | (has_kink & (hv < hn - (27 << 20)));
+                    }
                 }
                 if (guard) {   // one (rare) branch for the four elements: direct differences where needed
 #pragma unroll
@@ -309,8 +327,8 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                     const DevLeaf& lf = kp.leaves[l];
                     const int lk = SH::leaf_kind(kp, l), air = SH::leaf_arg_is_r(kp, l);
                     double vl[4];
-                    if (SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], vl);
-                    else leaf_value_vec_k<4>(lf, lk, air, s[1], vl);
+                    if (GG == 1 || SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], vl);
+                    else leaf_value_vec_k<4>(lf, lk, air, s[GG - 1], vl);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) out[e] = fma(mult[l], vl[e], out[e]);
                 }
@@ -324,8 +342,8 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                 if (l < SH::n_leaves(kp)) {
                     const DevLeaf& lf = kp.leaves[l];
                     const int lk = SH::leaf_kind(kp, l), air = SH::leaf_arg_is_r(kp, l);
-                    if (SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], v[l]);
-                    else leaf_value_vec_k<4>(lf, lk, air, s[1], v[l]);
+                    if (GG == 1 || SH::leaf_group(kp, l) == 0) leaf_value_vec_k<4>(lf, lk, air, s[0], v[l]);
+                    else leaf_value_vec_k<4>(lf, lk, air, s[GG - 1], v[l]);
                 }
             }
 #pragma unroll TU
@@ -561,14 +579,17 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
 #define GPB_GRAM_LAUNCH(DPV)                                                                                            \
     {                                                                                                                    \
         static bool attr_set = false;                                                                                    \
-        constexpr int SM = GramSmem<DPV>::TOTAL * (int)sizeof(double);                                                   \
+        using SHL = GPB_SH_FOR(DPV);                                                                                     \
+        using GS = GramSmem<DPV, gram_groups_of<SHL>()>;                                                                 \
+        constexpr int SM = GS::TOTAL * (int)sizeof(double);                                                              \
+        const int sm_now = (mode == 2 ? GS::TOTAL : GS::STAGE) * (int)sizeof(double);                                    \
         if (!attr_set) {                                                                                                 \
             e = cudaFuncSetAttribute(assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)>,                                         \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SM);                                   \
             attr_set = true;                                                                                             \
         }                                                                                                                \
         if (e == cudaSuccess)                                                                                            \
-            assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)><<<(unsigned)nblk, ASM_THREADS, SM, h->stream>>>(                  \
+            assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)><<<(unsigned)nblk, ASM_THREADS, sm_now, h->stream>>>(              \
                 kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n, has_kink);                                   \
     }
 #define GPB_SHAPE_BODY_                                  \

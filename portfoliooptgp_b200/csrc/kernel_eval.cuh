@@ -45,13 +45,12 @@ __device__ __forceinline__ void exp_vec(double (&x)[V]) {
     const double l2e = GPB_EXPK[0], ln2h = GPB_EXPK[1], ln2l = GPB_EXPK[2], magic = GPB_EXPK[3];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        // |x| >= 704 (incl. inf / NaN): out of the fast range, fixed up below; evaluate a harmless argument
-        const bool big = hi_abs(x[v]) >= 0x40860000;
-        const double xc = big ? 0.0 : x[v];
-        const double t = fma(xc, l2e, magic);
+        // |x| >= 704 (incl. inf / NaN) is out of the fast range: whatever this computes for it is
+        // discarded by the fix-up branch below (no traps on the device, so garbage in flight is harmless)
+        const double t = fma(x[v], l2e, magic);
         k[v] = __double2loint(t);
         const double n = t - magic;
-        r[v] = fma(n, -ln2l, fma(n, -ln2h, xc));
+        r[v] = fma(n, -ln2l, fma(n, -ln2h, x[v]));
         p[v] = GPB_EXPC[13];
     }
 #pragma unroll
