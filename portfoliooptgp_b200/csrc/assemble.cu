@@ -159,6 +159,13 @@ __host__ __device__ constexpr int gram_groups_of() {
     else return GRAM_GROUPS;
 }
 
+// resident CTAs per SM to compile for: single-leaf straight-line kernels fit 64 registers
+template <class SH>
+__host__ __device__ constexpr int gram_min_blocks() {
+    if constexpr (SH::is_static) return SH::NL == 1 ? 4 : 3;
+    else return 3;
+}
+
 template <int DP, int GG = GRAM_GROUPS>
 struct GramSmem {
     static constexpr int DPP = (DP % 8 == 0) ? DP + 4 : DP;   // row stride: conflict-free fragment loads
@@ -171,7 +178,7 @@ struct GramSmem {
 };
 
 template <int DP, class SH = DynShape>
-__global__ void __launch_bounds__(ASM_THREADS, 3)
+__global__ void __launch_bounds__(ASM_THREADS, gram_min_blocks<SH>())
 assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restrict__ X, int64_t N,
                      const double* __restrict__ X2, int64_t N2, int D, double* __restrict__ Kout, int64_t ldk, int mode,
                      double diag_add, int tiles_n, int has_kink_rt) {
