@@ -475,10 +475,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 (batched) and C5 (SVGP) side measurements")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+    # to stdout when the box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the whole run
+    # and the JSON line goes to the saved original.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
