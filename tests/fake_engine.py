@@ -117,3 +117,28 @@ class FakeEngine:
         m, v = O.gpr_predict_f(k, self.X, self.Y, noise, Xs)
         _arr(dmean, (Ns,))[:] = m[:, 0]
         _arr(dvar, (Ns,))[:] = v[:, 0]
+
+    # ---- SGPR (gpb_sgpr_elbo / gpb_sgpr_predict_f) -----------------------------------------------
+    def sgpr_elbo(self, theta, noise, dZ, M, D, dX, derr, N, n_params, want_grad, derrbar=None):
+        from oracle import gpflow_oracle_torch as T
+        k, leaves = self._kernel(theta)
+        Z, X, err = _arr(dZ, (M, D)).copy(), _arr(dX, (N, D)).copy(), _arr(derr, (N, 1)).copy()
+        out = np.zeros(2 + n_params + M * D)
+        self.launches += 1
+        if not want_grad:
+            out[0] = O.sgpr_elbo(k, Z, noise, X, err)
+            return out
+        e, g = T.sgpr_elbo_and_grad(k, Z, noise, X, err)
+        out[0], out[1] = e, g["noise"]
+        out[2:2 + n_params] = grad_to_theta_order(self.spec, leaves, k, g["theta"])
+        out[2 + n_params:] = g["Z"].reshape(-1)
+        if derrbar is not None:
+            _arr(derrbar, (N,))[:] = g["err"]
+        return out
+
+    def sgpr_predict_f(self, theta, noise, dZ, M, D, dX, derr, N, dXs, Ns, dmean, dvar):
+        k, _ = self._kernel(theta)
+        Z, X, err = _arr(dZ, (M, D)).copy(), _arr(dX, (N, D)).copy(), _arr(derr, (N, 1)).copy()
+        m, v = O.sgpr_predict_f(k, Z, noise, X, err, _arr(dXs, (Ns, D)))
+        _arr(dmean, (Ns,))[:] = m[:, 0]
+        _arr(dvar, (Ns,))[:] = v[:, 0]

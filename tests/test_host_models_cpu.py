@@ -120,3 +120,49 @@ def test_train_likelihood_restarts_pattern_and_deepcopy(fake):
     assert float(composite.kernels[0].variance.numpy()) == 1.0     # the template kernel was deep-copied, not trained
     m2 = copy.deepcopy(best_model)
     assert float(m2.training_loss()) == pytest.approx(float(best_model.training_loss()), rel=1e-12)
+
+
+def test_sgpr_host_layer_against_fake_engine(fake):
+    """models.SGPR on the CPU: objective sign, variable order (Z, kernel, noise, mean function),
+    softplus chain rule, the err = Y - m(X) sign of the mean-function gradient, predict_f / predict_y,
+    and the reference's plot_model pattern (test_scripts/SVGP.py:393-399) with SciPy."""
+    rng = np.random.default_rng(4)
+    N, D, M = 80, 2, 9
+    X, Y = make_multi_input(9, N, D)
+    Z0 = X[rng.choice(N, M, replace=False)].copy()
+    A0, b0 = np.array([[0.2], [-0.1]]), np.array([0.05])
+    k = gpflow.kernels.SquaredExponential(variance=0.9, lengthscales=1.2)
+    mf = gpflow.mean_functions.Linear(A=A0, b=b0)
+    m = gpflow.models.SGPR((X, Y), kernel=k, inducing_variable=Z0, noise_variance=0.1, mean_function=mf)
+    ko = to_oracle(k)
+    mean = X @ A0 + b0
+    want = O.sgpr_elbo(ko, Z0, 0.1, X, Y, mean=mean)
+    assert float(m.elbo()) == pytest.approx(want, rel=1e-12)
+    assert float(m.training_loss()) == pytest.approx(-want, rel=1e-12)
+    tv = m.trainable_variables
+    assert tv[0] is m.inducing_variable.Z.unconstrained_variable
+    loss, grads = m.training_loss_closure().value_and_grads(tv)
+    # finite differences of the oracle objective in UNCONSTRAINED space, variable by variable
+    def loss_at():
+        kk = to_oracle(k)
+        mm = X @ mf.A.numpy() + mf.b.numpy()
+        return -O.sgpr_elbo(kk, m.inducing_variable.Z.numpy(), float(m.likelihood.variance.numpy()), X, Y, mean=mm)
+    for v, g in zip(tv, grads):
+        flat = v._value.reshape(-1)
+        for idx in (0, flat.size - 1):
+            old = flat[idx]
+            h = 1e-6
+            flat[idx] = old + h; fp = loss_at()
+            flat[idx] = old - h; fm_ = loss_at()
+            flat[idx] = old
+            fd = (fp - fm_) / (2 * h)
+            assert np.ravel(g)[idx] == pytest.approx(fd, rel=2e-5, abs=2e-6)
+    Xs = rng.normal(size=(11, D))
+    fm, fv = m.predict_f(Xs)
+    om, ov = O.sgpr_predict_f(ko, Z0, 0.1, X, Y, Xs, mean=mean)
+    np.testing.assert_allclose(np.asarray(fm), om + Xs @ A0 + b0, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.asarray(fv), ov, rtol=1e-12, atol=1e-14)
+    ym, yv = m.predict_y(Xs)
+    np.testing.assert_allclose(np.asarray(yv), ov + 0.1, rtol=1e-12)
+    res = gpflow.optimizers.Scipy().minimize(m.training_loss, m.trainable_variables, options=dict(maxiter=15))
+    assert res.fun < loss
