@@ -48,75 +48,75 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     m = maxcor
     factr = ftol / np.finfo(float).eps
 
-    class _State:
-        __slots__ = ("x", "f", "g", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave", "nit", "nfev", "done")
-
-    states = []
+    # State of all problems in 2-D arrays; setulb gets ROW VIEWS of them (contiguous), so that the only
+    # per-problem Python work in a round is the setulb call itself and scattering / gathering x, f, g is
+    # vectorised.  Profile (5120 problems, n = 5): setulb takes ~13 us per call, two calls per problem
+    # and round, i.e. ~95 ms of host time per round against 2.5 ms on the device -- SciPy's own
+    # arithmetic is what bounds a full lock-step fit; it is kept because it reproduces scipy.optimize's
+    # iterates bit for bit.
+    X = np.array(X0, dtype=np.float64)
+    F = np.zeros((B,), dtype=np.float64)
+    G = np.zeros((B, n), dtype=np.float64)
+    WA = np.zeros((B, 2 * m * n + 5 * n + 11 * m * m + 8 * m), dtype=np.float64)
+    IWA = np.zeros((B, 3 * n), dtype=int_dtype)
+    TASK = np.zeros((B, 2), dtype=int_dtype)
+    LN_TASK = np.zeros((B, 2), dtype=int_dtype)
+    LSAVE = np.zeros((B, 4), dtype=int_dtype)
+    ISAVE = np.zeros((B, 44), dtype=int_dtype)
+    DSAVE = np.zeros((B, 29), dtype=np.float64)
+    NIT = np.zeros((B,), dtype=np.int64)
+    NFEV = np.zeros((B,), dtype=np.int64)
     nbd = np.zeros(n, dtype=int_dtype)
     low = np.zeros(n, dtype=np.float64)
     up = np.zeros(n, dtype=np.float64)
-    for b in range(B):
-        s = _State()
-        s.x = np.array(X0[b], dtype=np.float64)
-        s.f = np.array(0.0, dtype=np.float64)
-        s.g = np.zeros((n,), dtype=np.float64)
-        s.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
-        s.iwa = np.zeros(3 * n, dtype=int_dtype)
-        s.task = np.zeros(2, dtype=int_dtype)
-        s.ln_task = np.zeros(2, dtype=int_dtype)
-        s.lsave = np.zeros(4, dtype=int_dtype)
-        s.isave = np.zeros(44, dtype=int_dtype)
-        s.dsave = np.zeros(29, dtype=np.float64)
-        s.nit = 0
-        s.nfev = 0
-        s.done = False
-        states.append(s)
+    args = [(m, X[b], low, up, nbd, F[b:b + 1].reshape(()), G[b], factr, gtol, WA[b], IWA[b], TASK[b], LSAVE[b], ISAVE[b],
+             DSAVE[b], maxls, LN_TASK[b]) for b in range(B)]
+    setulb = _lbfgsb.setulb
 
     active = list(range(B))
     while active:
         waiting = []
         for b in active:
-            s = states[b]
+            a = args[b]
+            task = a[11]
             while True:  # advance until this problem needs f,g or stops
-                _lbfgsb.setulb(m, s.x, low, up, nbd, s.f, s.g, factr, gtol, s.wa, s.iwa, s.task, s.lsave, s.isave,
-                               s.dsave, maxls, s.ln_task)
-                if s.task[0] == 3:
+                setulb(*a)
+                t0 = task[0]
+                if t0 == 3:
                     waiting.append(b)
                     break
-                elif s.task[0] == 1:
-                    s.nit += 1
-                    if s.nit >= maxiter:
-                        s.task[0] = 5
-                        s.task[1] = 504
-                    elif s.nfev > maxfun:
-                        s.task[0] = 5
-                        s.task[1] = 502
+                elif t0 == 1:
+                    NIT[b] += 1
+                    if NIT[b] >= maxiter:
+                        task[0] = 5
+                        task[1] = 504
+                    elif NFEV[b] > maxfun:
+                        task[0] = 5
+                        task[1] = 502
                 else:
-                    s.done = True
                     break
         if not waiting:
             break
         idx = np.asarray(waiting, dtype=np.int64)
-        Xb = np.stack([states[b].x for b in waiting])
-        fb, gb = fun_batch(Xb, idx)
-        for k, b in enumerate(waiting):
-            s = states[b]
-            s.f = np.array(float(fb[k]), dtype=np.float64)
-            s.g = np.ascontiguousarray(gb[k], dtype=np.float64)
-            s.nfev += 1
+        fb, gb = fun_batch(X[idx], idx)
+        F[idx] = np.asarray(fb, dtype=np.float64)
+        G[idx] = np.asarray(gb, dtype=np.float64)
+        NFEV[idx] += 1
         active = waiting
 
     results = []
-    for s in states:
-        if s.task[0] == 4:
+    for b in range(B):
+        t0, t1 = int(TASK[b, 0]), int(TASK[b, 1])
+        nit, nfev = int(NIT[b]), int(NFEV[b])
+        if t0 == 4:
             warnflag = 0
-        elif s.nfev > maxfun or s.nit >= maxiter:
+        elif nfev > maxfun or nit >= maxiter:
             warnflag = 1
         else:
             warnflag = 2
-        msg = _lb.status_messages[s.task[0]] + ": " + _lb.task_messages[s.task[1]]
-        results.append(scipy.optimize.OptimizeResult(fun=float(s.f), jac=s.g, nfev=s.nfev, njev=s.nfev, nit=s.nit,
-                                                     status=warnflag, message=msg, x=s.x, success=(warnflag == 0)))
+        msg = _lb.status_messages[t0] + ": " + _lb.task_messages[t1]
+        results.append(scipy.optimize.OptimizeResult(fun=float(F[b]), jac=G[b].copy(), nfev=nfev, njev=nfev, nit=nit,
+                                                     status=warnflag, message=msg, x=X[b].copy(), success=(warnflag == 0)))
     return results
 
 
