@@ -326,7 +326,23 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
         }
         // leaves, four elements at a time
         double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (pure_sum) {
+        if constexpr (SH::FUSED2) {
+            // v0 f0 * v1 f1 = v0 v1 exp(arg0 + arg1): one exponential for the product of two leaves
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double dummy;
+                    a[e] += pure_exp_arg<false>(kp.leaves[l], SH::leaf_kind(kp, l),
+                                                (GG == 1 || SH::leaf_group(kp, l) == 0) ? s[0][e] : s[GG - 1][e], dummy);
+                }
+            }
+            exp_vec<4>(a);
+            const double vv = kp.leaves[0].variance * kp.leaves[1].variance;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[e] = vv * a[e];
+        } else if (pure_sum) {
             // K = sum_l mult_l * leaf_l : accumulate straight into the outputs, no per-leaf arrays, no selects
 #pragma unroll
             for (int l = 0; l < GRAD_FAST_LEAVES; ++l) {

@@ -136,6 +136,7 @@ struct DevKernel {
 struct DynShape {
     static constexpr bool is_static = false;
     static constexpr int HAS_KINK = 0;   // unused: the interpreter gets it as a kernel argument
+    static constexpr bool FUSED2 = false;
     static __host__ __device__ __forceinline__ int n_groups(const DevKernel& kp) { return kp.n_groups; }
     static __host__ __device__ __forceinline__ int group_kind(const DevKernel& kp, int g) { return kp.groups[g].kind; }
     static __host__ __device__ __forceinline__ int n_leaves(const DevKernel& kp) { return kp.n_leaves; }
@@ -162,6 +163,16 @@ struct StaticShape {
         return (c >= 0 && ((c & 15) == GPB_LEAF_MATERN12 || (c & 15) == GPB_LEAF_EXPONENTIAL)) ? 1 : 0;
     }
     static constexpr int HAS_KINK = kink_of(L0) | kink_of(L1) | kink_of(L2) | kink_of(L3);
+    // One product term of two "pure exponential" leaves (SE, Matern12, Exponential) on Euclidean groups:
+    // v0 f0 * v1 f1 = v0 v1 exp(arg0 + arg1) needs ONE exponential per element, and every parameter
+    // derivative is that value times a rational factor (k1 * k2 of Multi-Input_GPR/main.py:126-135 with
+    // both Exponential; SquaredExponential * Matern12 of GPR/main.py:113).
+    static __host__ __device__ constexpr bool pure_exp(int c) {
+        return c >= 0 && ((c & 15) == GPB_LEAF_SE || (c & 15) == GPB_LEAF_MATERN12 || (c & 15) == GPB_LEAF_EXPONENTIAL);
+    }
+    static constexpr bool FUSED2 = NL == 2 && NT == 1 && (T0 & 15) == 2 && ((T0 >> 4) & 15) == 0 && ((T0 >> 8) & 15) == 1 &&
+                                   pure_exp(L0) && pure_exp(L1) && G0 == GPB_GROUP_EUCLID &&
+                                   (G1 < 0 || G1 == GPB_GROUP_EUCLID);
     static __host__ __device__ constexpr int n_groups(const DevKernel&) { return NG; }
     static __host__ __device__ constexpr int group_kind(const DevKernel&, int g) { return g == 0 ? G0 : G1; }
     static __host__ __device__ constexpr int n_leaves(const DevKernel&) { return NL; }
@@ -493,6 +504,22 @@ __device__ __forceinline__ double sel4(const double (&a)[GRAD_FAST_LEAVES], int 
     return r;
 }
 
+// log f(u) of a pure-exponential leaf on a Euclidean group (u = s * scale = r^2) and, when GRAD,
+// d log f / d lengthscale:  SE: -u/2, u/l ;  Matern12: -r, r/l ;  Exponential: -r/2, r/(2 l)
+// (r clamped at 1e-18 like GPflow's sqrt(max(r2, 1e-36)); the derivative is then 1e-18/l ~ 0).
+template <bool GRAD>
+__device__ __forceinline__ double pure_exp_arg(const DevLeaf& lf, const int kind, double s, double& darg_dls) {
+    const double u = s * lf.scale;
+    if (kind == GPB_LEAF_SE) {
+        if (GRAD) darg_dls = u * lf.inv_ls;
+        return -0.5 * u;
+    }
+    const double r = (__double2hiint(u) < 0x38754484) ? 1e-18 : sqrt(u);
+    const double c = (kind == GPB_LEAF_MATERN12) ? 1.0 : 0.5;
+    if (GRAD) darg_dls = c * r * lf.inv_ls;
+    return -c * r;
+}
+
 // Forward value with the leaves statically unrolled (same structure as the gradient fast path): the
 // per-leaf constants sit at compile-time offsets of the kernel-parameter block, so the compiler
 // hoists them out of the element loops instead of chasing term -> leaf -> group indices per element.
@@ -584,6 +611,34 @@ __device__ __forceinline__ void leaf_value_vec(const DevLeaf& lf, const double (
 template <int DP, class SH = DynShape>
 __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const double (&xa)[DP], const double (&xb)[DP],
                                                  const double (&xj0)[DP], const double (&xj1)[DP], double (&out)[4]) {
+    if constexpr (SH::FUSED2) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        int g_prev = -1;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int gi = SH::leaf_group(kp, l);
+            if (gi != g_prev) {
+                double dummy;
+                const DevGroup& g = kp.groups[gi];
+                s[0] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xa, xj0, dummy);
+                s[1] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xa, xj1, dummy);
+                s[2] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xb, xj0, dummy);
+                s[3] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xb, xj1, dummy);
+                g_prev = gi;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                double dummy;
+                a[e] += pure_exp_arg<false>(kp.leaves[l], SH::leaf_kind(kp, l), s[e], dummy);
+            }
+        }
+        exp_vec<4>(a);
+        const double vv = kp.leaves[0].variance * kp.leaves[1].variance;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = vv * a[e];
+        return;
+    }
     double v[GRAD_FAST_LEAVES][4];
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     int g_prev = -1;
@@ -636,6 +691,28 @@ __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const doub
 template <int DP, class SH = DynShape>
 __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, const double (&xi)[DP],
                                                          const double (&xj)[DP], double wgt, GradAcc& A) {
+    if constexpr (SH::FUSED2) {
+        double arg = 0.0, dl[2], s_prev = 0.0;
+        int g_prev = -1;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int gi = SH::leaf_group(kp, l);
+            if (gi != g_prev) {
+                double dummy;
+                s_prev = group_value_k<DP, false>(kp.groups[gi], GPB_GROUP_EUCLID, xi, xj, dummy);
+                g_prev = gi;
+            }
+            arg += pure_exp_arg<true>(kp.leaves[l], SH::leaf_kind(kp, l), s_prev, dl[l]);
+        }
+        const double f = gpb_exp(arg);
+        const double v0 = kp.leaves[0].variance, v1 = kp.leaves[1].variance;
+        const double wf = wgt * f, k = v0 * v1 * f, wk = wgt * k;
+        A.var[0] = fma(wf, v1, A.var[0]);
+        A.var[1] = fma(wf, v0, A.var[1]);
+        A.ls[0] = fma(wk, dl[0], A.ls[0]);
+        A.ls[1] = fma(wk, dl[1], A.ls[1]);
+        return k;
+    }
     double v[GRAD_FAST_LEAVES], fval[GRAD_FAST_LEAVES], dls[GRAD_FAST_LEAVES], dal[GRAD_FAST_LEAVES],
         dper[GRAD_FAST_LEAVES], ladj[GRAD_FAST_LEAVES];
     double s_prev = 0.0, dsp_prev = 0.0;
