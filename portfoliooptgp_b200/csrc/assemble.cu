@@ -601,16 +601,12 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
         // one attribute call per instantiation (static flag inside the macro body's scope)
 #define GPB_GRAM_LAUNCH(DPV)                                                                                            \
     {                                                                                                                    \
-        static bool attr_set = false;                                                                                    \
+        static bool attr_set[GPB_MAX_DEVICES] = {};                                                                      \
         using SHL = GPB_SH_FOR(DPV);                                                                                     \
         using GS = GramSmem<DPV, gram_groups_of<SHL>()>;                                                                 \
         constexpr int SM = GS::TOTAL * (int)sizeof(double);                                                              \
         const int sm_now = (mode == 2 ? GS::TOTAL : GS::STAGE) * (int)sizeof(double);                                    \
-        if (!attr_set) {                                                                                                 \
-            e = cudaFuncSetAttribute(assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)>,                                         \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM);                                   \
-            attr_set = true;                                                                                             \
-        }                                                                                                                \
+        e = ensure_dyn_smem(attr_set, h->device, assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)>, (size_t)SM);                \
         if (e == cudaSuccess)                                                                                            \
             assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)><<<(unsigned)nblk, ASM_THREADS, sm_now, h->stream>>>(              \
                 kp, d_X, N, d_X2, N2, D, d_K, ldk, mode, diag_add, tiles_n, has_kink);                                   \

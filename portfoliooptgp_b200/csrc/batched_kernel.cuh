@@ -278,11 +278,10 @@ static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Y
                              const double* d_Xs, int Ns, double* d_mean, double* d_var) {
     auto kern = batched_gp_kernel<DP, FAST, SH>;
     constexpr size_t SMEM = batched_smem_bytes<DP>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    static bool attr_set[GPB_MAX_DEVICES] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(attr_set, h->device, kern, SMEM);
         if (e != cudaSuccess) return check_cuda(h, e, "batched cudaFuncSetAttribute");
-        attr_set = true;
     }
     static long long* d_prof = nullptr;   // GPB_BATCHED_PROF=1: phase cycle stamps of CTA 0 to stderr (debug)
     static int want_prof = -1;

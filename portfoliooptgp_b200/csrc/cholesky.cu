@@ -85,11 +85,10 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
 
 static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int n, int offset, double* logdiag,
                 int* info, bool store_L) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(leaf_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
+    static bool attr_set[GPB_MAX_DEVICES] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(attr_set, h->device, leaf_potrf_inv_kernel, LEAF_SMEM);
         if (e != cudaSuccess) return check_cuda(h, e, "leaf cudaFuncSetAttribute");
-        attr_set = true;
     }
     ProfScope prof(h, PROF_LEAF, h->stream);
     if (h->use_pdl) {

@@ -230,11 +230,10 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     constexpr int B_ST = BKC ? BN * (BK + 4) : BK * (BN + 4);
     constexpr size_t SMEM = (size_t)STAGES * (A_ST + B_ST) * sizeof(double);
     auto kern = dgemm_kernel<BM, BN, BK, WM, WN, STAGES, AKC, BKC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    static bool attr_set[GPB_MAX_DEVICES] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(attr_set, h->device, kern, SMEM);
         if (e != cudaSuccess) return check_cuda(h, e, "dgemm cudaFuncSetAttribute");
-        attr_set = true;
     }
     const int tm = (p.M + BM - 1) / BM, tn = (p.N + BN - 1) / BN;
     p.tiles_n = tn;

@@ -117,6 +117,18 @@ struct GemmArgs {
 };
 int launch_gemm(gpb_handle* h, const GemmArgs& a, cudaStream_t stream);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per function AND per device: a process that holds
+// engines on several GPUs must set it once on each.  One flag per device, per call site (the flag array
+// is a function-local static of the templated launcher, i.e. one per kernel instantiation).
+constexpr int GPB_MAX_DEVICES = 64;
+template <class K>
+inline cudaError_t ensure_dyn_smem(bool (&done)[GPB_MAX_DEVICES], int device, K kern, size_t bytes) {
+    if (device >= 0 && device < GPB_MAX_DEVICES && done[device]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && device >= 0 && device < GPB_MAX_DEVICES) done[device] = true;
+    return e;
+}
+
 // ---- cholesky.cu
 // A (lower, in place) -> L on the diagonal blocks (and everywhere when keepL), W = L^-1 (lower, zero
 // strict-upper inside 128-aligned diagonal blocks), logdiag[b] = sum of log L_ii over block b,

@@ -161,3 +161,23 @@ def test_mean_functions_train_and_predict(gp):
     before = float(m.training_loss())
     res = gp.optimizers.Scipy().minimize(m.training_loss, m.trainable_variables, options=dict(maxiter=30))
     assert res.fun < before
+
+
+def test_two_devices_in_one_process(gp):
+    """One process, engines on two GPUs (per-device kernel attributes, workspaces, streams): same answers."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    X, Y = make_multi_input(3, 700, 8)
+    k = gp.kernels.SquaredExponential() + gp.kernels.Matern52() + gp.kernels.Linear()
+    out = []
+    for dev in (0, 1):
+        m = gp.models.GPR((X, Y), kernel=k, noise_variance=1e-2, device=dev)
+        lml, g, gn = m.lml_and_constrained_grads()
+        fm, fv = m.predict_f(X[:40])
+        bg = gp.BatchedGPR(np.stack([X[i:i + 128] for i in range(4)]), np.stack([Y[i:i + 128, 0] for i in range(4)]), k,
+                           noise_variance=0.1, device=dev)
+        out.append((lml, g, gn, np.asarray(fm), np.asarray(fv), bg.lml_and_grads()[0]))
+    assert out[0][0] == out[1][0] and out[0][2] == out[1][2]
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4])
+    assert np.array_equal(out[0][5], out[1][5])
