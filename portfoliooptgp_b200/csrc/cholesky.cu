@@ -218,7 +218,9 @@ __global__ void trmv_lower_kernel(const double* __restrict__ W, int64_t ldw, int
 }
 
 // partial[c][j] = sum_{i in chunk c, i >= j} W[i][j] a[i]; chunks of CH rows; thread per column.
-constexpr int TRMVT_CH = 128;
+// (32-row chunks: at N = 1000 the 128-row version was one dependent load-FMA chain of 128 steps on 64
+// CTAs and took 56 us; short chunks give the grid enough CTAs and the unrolled loads overlap.)
+constexpr int TRMVT_CH = 32;
 __global__ void trmvT_partial_kernel(const double* __restrict__ W, int64_t ldw, int n, const double* __restrict__ a,
                                      double* __restrict__ partial) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,7 +228,16 @@ __global__ void trmvT_partial_kernel(const double* __restrict__ W, int64_t ldw, 
     if (j >= n) return;
     const int i0 = c * TRMVT_CH, i1 = min(n, i0 + TRMVT_CH);
     double s = 0.0;
-    for (int i = max(i0, j); i < i1; ++i) s = fma(W[(int64_t)i * ldw + j], a[i], s);
+    if (j <= i0 && i1 - i0 == TRMVT_CH) {
+        // full chunk below the diagonal: all loads issued before the (fixed-order) FMA chain
+        double w[TRMVT_CH];
+#pragma unroll
+        for (int k = 0; k < TRMVT_CH; ++k) w[k] = W[(int64_t)(i0 + k) * ldw + j];
+#pragma unroll
+        for (int k = 0; k < TRMVT_CH; ++k) s = fma(w[k], a[i0 + k], s);
+    } else {
+        for (int i = max(i0, j); i < i1; ++i) s = fma(W[(int64_t)i * ldw + j], a[i], s);
+    }
     partial[(int64_t)c * n + j] = s;
 }
 __global__ void colsum_partials_kernel(const double* __restrict__ partial, int nchunks, int n, double* __restrict__ out) {
