@@ -166,6 +166,19 @@ int gpb_gpr_lml_grad(gpb_handle* h, const double* h_theta, double noise_variance
 int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_variance, const double* d_Xs,
                       int64_t Ns, double* d_mean, double* d_var);
 
+/* predict_f that may skip the factorisation.  gpb_gpr_factor_serial(h) identifies the factorisation the
+ * last gpb_gpr_lml / gpb_gpr_lml_grad / gpb_gpr_predict_f call left in the handle's workspaces.  A caller
+ * that reads it right after its own call and passes it back here gets W = L^-1 reused when the kernel
+ * expression, theta, noise and the bound X (pointer, N, D) are bit-identical and nothing else has used the
+ * workspaces in between; otherwise the call silently does the full work (same results either way).  The
+ * engine cannot see the memory behind the X pointer: that its CONTENT is unchanged is the caller's
+ * guarantee (the host layer keeps the tensor alive in the model object).  Use: GPflow's predict_y
+ * recomputes predict_f, and the reference calls both back to back (GPR/predictor.py:6-7). */
+int64_t gpb_gpr_factor_serial(gpb_handle* h);
+int gpb_gpr_predict_f_reuse(gpb_handle* h, const double* h_theta, double noise_variance,
+                            int64_t factor_serial, const double* d_Xs, int64_t Ns, double* d_mean,
+                            double* d_var);
+
 /* d_alpha [N] <- (K + noise I)^-1 (Y - m(X)) of the last gpb_gpr_lml / gpb_gpr_lml_grad / gpb_gpr_predict_f
  * evaluation on this handle (= dLML/dm(X); lets the host layer train mean-function parameters,
  * test_scripts/GPFlow.py:186-190 uses Constant / Linear mean functions).  Asynchronous. */

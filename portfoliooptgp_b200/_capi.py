@@ -93,6 +93,8 @@ SIGNATURES = {
     "gpb_svgp_data_term": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _P, _I64, _P, _INT]),
     "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
     "gpb_svgp_predict_f": (_INT, [_P, _DP, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
+    "gpb_gpr_factor_serial": (_I64, [_P]),
+    "gpb_gpr_predict_f_reuse": (_INT, [_P, _DP, _D, _I64, _P, _I64, _P, _P]),
     "gpb_sgpr_elbo": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _INT, _DP, _P]),
     "gpb_sgpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _P]),
     "gpb_adam_step": (_INT, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _I64, _INT]),
@@ -312,6 +314,13 @@ class Engine:
     def prep_windows(self, dfeat: int, dy: int, S: int, T: int, D: int, N: int, stride: int, dX: int, dY: int):
         self._check(self._lib.gpb_prep_windows(self._h, _P(dfeat), _P(dy), S, T, D, N, stride, _P(dX), _P(dY)),
                     "gpb_prep_windows")
+
+    def gpr_factor_serial(self) -> int:
+        return int(self._lib.gpb_gpr_factor_serial(self._h))
+
+    def gpr_predict_f_reuse(self, theta, noise: float, serial: int, dXs: int, Ns: int, dmean: int, dvar: int):
+        self._check(self._lib.gpb_gpr_predict_f_reuse(self._h, _as_dp(theta), float(noise), int(serial), _P(dXs), Ns,
+                                                      _P(dmean), _P(dvar)), "gpb_gpr_predict_f_reuse")
 
     def gpr_get_alpha(self, dalpha: int):
         self._check(self._lib.gpb_gpr_get_alpha(self._h, _P(dalpha)), "gpb_gpr_get_alpha")

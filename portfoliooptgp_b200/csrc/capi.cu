@@ -27,6 +27,9 @@ int check_cuda(gpb_handle* h, cudaError_t e, const char* what) {
 }
 
 double* workspace(gpb_handle* h, int id, size_t bytes) {
+    // whoever asks for these three is about to overwrite the stored GPR factorisation (gpr.cu re-validates
+    // it after its own requests)
+    if (id == BUF_K || id == BUF_W || id == BUF_VEC) h->fact_valid = false;
     if (bytes <= h->buf_bytes[id] && h->buf[id]) return h->buf[id];
     if (h->buf[id]) {
         cudaFree(h->buf[id]);  // synchronises the device: no kernel can still be using the old block
@@ -369,6 +372,15 @@ int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_varianc
     GPB_ENTER(h);
     if (!h_theta || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "predict_f: null pointer");
     return gpr_predict_f(h, h_theta, noise_variance, d_Xs, Ns, d_mean, d_var);
+}
+
+int64_t gpb_gpr_factor_serial(gpb_handle* h) { return h ? h->fact_serial : -1; }
+
+int gpb_gpr_predict_f_reuse(gpb_handle* h, const double* h_theta, double noise_variance, int64_t factor_serial,
+                            const double* d_Xs, int64_t Ns, double* d_mean, double* d_var) {
+    GPB_ENTER(h);
+    if (!h_theta || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "predict_f_reuse: null pointer");
+    return gpr_predict_f(h, h_theta, noise_variance, d_Xs, Ns, d_mean, d_var, factor_serial);
 }
 
 }  // extern "C"

@@ -21,6 +21,17 @@ struct gpb_handle {
     bool fork_streams = true;   // gpb_set_option(h, 0, x)
     bool use_pdl = true;        // gpb_set_option(h, 1, x): programmatic dependent launch for dgemm / leaf
     bool use_shapes = true;     // gpb_set_option(h, 2, x): straight-line kernels for the known expression shapes (shapes.cuh)
+    // the factorisation W = L^-1, a = W y left in the workspaces by the last gpr_lml / gpr_predict_f:
+    // what it was computed for, and whether the workspaces still hold it (any other use of BUF_K / BUF_W /
+    // BUF_VEC clears the flag).  fact_serial counts factorisations; gpb_gpr_predict_f_reuse consumes it.
+    bool fact_valid = false;
+    int64_t fact_serial = 0;
+    const double* fact_X = nullptr;
+    int64_t fact_N = 0;
+    int fact_D = 0;
+    double fact_noise = 0.0;
+    double fact_theta[GPB_MAX_PARAMS] = {};
+    gpb_kernel_spec fact_spec = {};
     int64_t launches = 0;
     int sm_count = 148;
 
@@ -147,7 +158,7 @@ int predict_colreduce(gpb_handle* h, const double* A, int64_t lda, int64_t n, in
 int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, double* grad_theta, double* grad_noise,
             int want_grad);
 int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double* d_Xs, int64_t Ns, double* d_mean,
-                  double* d_var);
+                  double* d_var, int64_t reuse_serial = -1);
 
 // ---- batched.cu: one GP per CTA.  mode 0 = LML, 1 = LML + gradient, 2 = predict_f
 int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta, const double* d_noise,

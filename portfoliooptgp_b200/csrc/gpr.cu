@@ -16,6 +16,7 @@
 //   5. g_p = sum_{i>=j} c_ij (alpha_i alpha_j - K^-1_ij) dK_ij/dtheta_p   (fused, dK never stored)
 //   6. LML = -quad/2 - N/2 log 2pi - logdet ; dLML/dtheta_p = g_p / 2 ; dLML/dnoise = tr(.)/2
 #include <math.h>
+#include <string.h>
 
 #include "engine.cuh"
 
@@ -46,11 +47,33 @@ static int gpr_workspaces(gpb_handle* h, GprWork* w) {
     return 0;
 }
 
-// steps 1-3; leaves W, a, alpha, res[0..1], info on the device
-static int gpr_factor(gpb_handle* h, const DevKernel& kp, double noise, GprWork& w) {
+// Is the factorisation in the workspaces the one for (current spec, theta, noise, bound X)?  The engine can
+// only compare what it sees (pointer, sizes, parameters); that the CONTENT behind the X pointer is unchanged
+// is the caller's guarantee, given by passing the serial it read after its own factorisation.
+static bool factor_matches(const gpb_handle* h, bool was_valid, const double* theta, double noise, int64_t serial) {
+    if (!was_valid || serial < 0 || serial != h->fact_serial) return false;
+    if (h->fact_X != h->d_X || h->fact_N != h->N || h->fact_D != h->D || h->fact_noise != noise) return false;
+    if (memcmp(&h->fact_spec, &h->spec, sizeof(gpb_kernel_spec)) != 0) return false;
+    return memcmp(h->fact_theta, theta, sizeof(double) * (size_t)h->spec.n_params) == 0;
+}
+
+static void factor_remember(gpb_handle* h, const double* theta, double noise) {
+    h->fact_valid = true;
+    h->fact_serial += 1;
+    h->fact_X = h->d_X; h->fact_N = h->N; h->fact_D = h->D; h->fact_noise = noise;
+    h->fact_spec = h->spec;
+    memset(h->fact_theta, 0, sizeof(h->fact_theta));
+    memcpy(h->fact_theta, theta, sizeof(double) * (size_t)h->spec.n_params);
+}
+
+// steps 1-3; leaves W, a, alpha, res[0..1], info on the device.  reuse: W and the log-det partials of the
+// previous call are still valid, only the vectors (which depend on the bound Y) are recomputed.
+static int gpr_factor(gpb_handle* h, const DevKernel& kp, double noise, GprWork& w, bool reuse = false) {
     int rc;
-    if ((rc = launch_assemble(h, kp, h->d_X, h->N, h->d_X, h->N, h->D, w.A, w.ld, 1, noise))) return rc;
-    if ((rc = factor_inv(h, w.A, w.ld, w.W, w.ld, h->N, w.logdiag, w.info, false))) return rc;
+    if (!reuse) {
+        if ((rc = launch_assemble(h, kp, h->d_X, h->N, h->d_X, h->N, h->D, w.A, w.ld, 1, noise))) return rc;
+        if ((rc = factor_inv(h, w.A, w.ld, w.W, w.ld, h->N, w.logdiag, w.info, false))) return rc;
+    }
     if ((rc = trmv_lower(h, w.W, w.ld, h->N, h->d_Yc, w.a))) return rc;
     if ((rc = trmv_lower_T(h, w.W, w.ld, h->N, w.a, w.alpha))) return rc;
     return quad_logdet(h, w.a, h->N, w.logdiag, w.res);
@@ -68,6 +91,7 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
     GprWork w;
     if ((rc = gpr_workspaces(h, &w))) return rc;
     if ((rc = gpr_factor(h, kp, noise, w))) return rc;
+    factor_remember(h, theta, noise);   // (a failed pivot invalidates it again below)
     const int P = kp.n_params;
     if (want_grad) {
         if ((rc = lauum_lower(h, w.W, h->N, w.ld, w.A, w.ld))) return rc;
@@ -83,6 +107,7 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
     if (e != cudaSuccess) return check_cuda(h, e, "gpr result copy/sync");
     const int info = *reinterpret_cast<int*>(hp + 64);
     if (info > 0) {
+        h->fact_valid = false;
         set_error(h, info, "Cholesky decomposition was not successful: non-positive pivot at row %d of %lld", info,
                   (long long)h->N);
         return info;
@@ -96,16 +121,20 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
 }
 
 int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double* d_Xs, int64_t Ns, double* d_mean,
-                  double* d_var) {
+                  double* d_var, int64_t reuse_serial) {
     if (!h->has_spec) return set_error(h, -3, "predict_f: no kernel set");
     if (!h->d_X || h->N <= 0) return set_error(h, -3, "predict_f: no data bound");
     if (Ns <= 0) return 0;
     DevKernel kp;
     int rc = build_dev_kernel(h, theta, &kp);
     if (rc) return rc;
+    const bool was_valid = h->fact_valid;   // (the workspace requests below clear the flag)
     GprWork w;
     if ((rc = gpr_workspaces(h, &w))) return rc;
-    if ((rc = gpr_factor(h, kp, noise, w))) return rc;
+    const bool reuse = factor_matches(h, was_valid, theta, noise, reuse_serial);
+    if ((rc = gpr_factor(h, kp, noise, w, reuse))) return rc;
+    if (reuse) h->fact_valid = true;        // same factorisation, same serial
+    else factor_remember(h, theta, noise);
     const int64_t N = h->N;
     // chunk the test points so that the two [N, chunk] work matrices stay near 1 GiB each
     int64_t chunk = (int64_t)(1 << 27) / (N > 0 ? N : 1);
@@ -136,6 +165,7 @@ int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double
     if (e != cudaSuccess) return check_cuda(h, e, "predict_f sync");
     const int info = *reinterpret_cast<int*>(hp + 64);
     if (info > 0) {
+        h->fact_valid = false;
         set_error(h, info, "Cholesky decomposition was not successful: non-positive pivot at row %d of %lld", info,
                   (long long)N);
         return info;
@@ -152,7 +182,9 @@ namespace gpb {
 int gpr_get_alpha(gpb_handle* h, double* d_alpha) {
     if (!h->d_X || h->N <= 0) return set_error(h, -3, "get_alpha: no data bound");
     GprWork w;
+    const bool keep = h->fact_valid;   // read-only use of the workspaces
     int rc = gpr_workspaces(h, &w);
+    h->fact_valid = keep;
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(d_alpha, w.alpha, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
     return check_cuda(h, e, "get_alpha copy");

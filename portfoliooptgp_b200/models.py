@@ -89,7 +89,7 @@ class GPModel(Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in vars(self).items():
-            if k in ("_engine", "_compiled", "_compiled_token"):
+            if k in ("_engine", "_compiled", "_compiled_token", "_fact"):
                 setattr(new, k, None)
             elif isinstance(v, torch.Tensor):
                 setattr(new, k, v)  # device data is immutable here: share it
@@ -164,6 +164,10 @@ class GPR(GPModel):
             raise NotImplementedError("only single-output Y [N,1] is supported (R = 1 on every reference call site)")
         self.data = (Xd, Yd)
         self._Yc: Optional[torch.Tensor] = None
+        # (engine, factorisation serial) of this model's own last evaluation: predict_f hands it back so that
+        # the engine can reuse W = L^-1 when theta / noise are unchanged (predict_y after predict_f, predict
+        # after the last objective evaluation).  Safe because this object keeps X alive and immutable.
+        self._fact: Optional[Tuple[int, int]] = None
 
     # -- binding -------------------------------------------------------------------------------
     def _bind(self) -> Tuple[_capi.Engine, CompiledKernel]:
@@ -182,9 +186,14 @@ class GPR(GPModel):
         return float(self.likelihood.variance.numpy())
 
     # -- objective -----------------------------------------------------------------------------
+    def _remember_factor(self, eng):
+        self._fact = (id(eng), eng.gpr_factor_serial()) if hasattr(eng, "gpr_factor_serial") else None
+
     def log_marginal_likelihood(self):
         eng, ck = self._bind()
-        return torch.tensor(eng.gpr_lml(ck.theta(), self._noise()), dtype=torch.float64)
+        lml = eng.gpr_lml(ck.theta(), self._noise())
+        self._remember_factor(eng)
+        return torch.tensor(lml, dtype=torch.float64)
 
     def maximum_log_likelihood_objective(self):
         return self.log_marginal_likelihood()
@@ -197,11 +206,14 @@ class GPR(GPModel):
     def lml_and_constrained_grads(self):
         """(lml, d lml/d theta [constrained, engine order], d lml/d noise_variance)."""
         eng, ck = self._bind()
-        return eng.gpr_lml_grad(ck.theta(), self._noise())
+        out = eng.gpr_lml_grad(ck.theta(), self._noise())
+        self._remember_factor(eng)
+        return out
 
     def _training_loss_and_grads(self, variables: Sequence[Variable], data=None):
         eng, ck = self._bind()
         lml, g_theta, g_noise = eng.gpr_lml_grad(ck.theta(), self._noise())
+        self._remember_factor(eng)
         by_param = ck.scatter_grad(g_theta)
         pv = self.likelihood.variance
         by_param[id(pv)] = np.asarray(g_noise) * pv.transform.forward_grad(pv.unconstrained_variable._value)
@@ -223,7 +235,12 @@ class GPR(GPModel):
             raise ValueError(f"Xnew has {Xs.shape[1]} columns, the model was built with {self.data[0].shape[1]}")
         Ns = Xs.shape[0]
         out = torch.empty((2, Ns), dtype=torch.float64, device=Xs.device)
-        eng.gpr_predict_f(ck.theta(), self._noise(), Xs.data_ptr(), Ns, out[0].data_ptr(), out[1].data_ptr())
+        if self._fact is not None and self._fact[0] == id(eng) and hasattr(eng, "gpr_predict_f_reuse"):
+            eng.gpr_predict_f_reuse(ck.theta(), self._noise(), self._fact[1], Xs.data_ptr(), Ns, out[0].data_ptr(),
+                                    out[1].data_ptr())
+        else:
+            eng.gpr_predict_f(ck.theta(), self._noise(), Xs.data_ptr(), Ns, out[0].data_ptr(), out[1].data_ptr())
+        self._remember_factor(eng)
         mean = out[0][:, None]
         if not isinstance(self.mean_function, Zero):
             mean = mean + self.mean_function(Xs)

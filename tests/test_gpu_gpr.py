@@ -181,3 +181,53 @@ def test_two_devices_in_one_process(gp):
     assert out[0][0] == out[1][0] and out[0][2] == out[1][2]
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4])
     assert np.array_equal(out[0][5], out[1][5])
+
+
+def test_predict_reuses_the_factorisation_only_when_it_may(gp):
+    """predict_y after predict_f (GPR/predictor.py:6-7), and predict after an objective evaluation at the
+    same theta, skip the factorisation (fewer launches, identical numbers); another model in between, a
+    parameter change or new data force the full path."""
+    X, Y = make_multi_input(8, 900, 3)
+    Xs = np.random.default_rng(2).normal(size=(60, 3))
+    k = gp.kernels.SquaredExponential(lengthscales=0.9) + gp.kernels.Matern12(variance=0.4)
+    m = gp.models.GPR((X, Y), kernel=k, noise_variance=0.05)
+    eng = m._get_engine()
+
+    def launches(fn):
+        n0 = eng.launch_count()
+        out = fn()
+        return out, eng.launch_count() - n0
+
+    (f1, v1), n_full = launches(lambda: m.predict_f(Xs))
+    (f2, v2), n_reuse = launches(lambda: m.predict_f(Xs))
+    assert n_reuse < n_full - 5, (n_full, n_reuse)
+    assert np.array_equal(np.asarray(f1), np.asarray(f2)) and np.array_equal(np.asarray(v1), np.asarray(v2))
+    (ym, yv), n_y = launches(lambda: m.predict_y(Xs))
+    assert n_y == n_reuse
+    np.testing.assert_allclose(np.asarray(yv), np.asarray(v1) + 0.05, rtol=1e-15)
+    # objective evaluation, then predict at the same theta: reuse
+    m.training_loss_closure().value_and_grads(m.trainable_variables)
+    (f3, v3), n3 = launches(lambda: m.predict_f(Xs))
+    assert n3 == n_reuse and np.array_equal(np.asarray(f3), np.asarray(f1)) and np.array_equal(np.asarray(v3), np.asarray(v1))
+    # another model on the same engine in between: full path, still the right answer
+    other = gp.models.GPR((X[:500], Y[:500]), kernel=gp.kernels.Matern32(), noise_variance=0.1)
+    other.predict_f(Xs)
+    (f4, v4), n4 = launches(lambda: m.predict_f(Xs))
+    assert n4 == n_full and np.array_equal(np.asarray(f4), np.asarray(f1))
+    # parameter change: full path, different answer, matches a fresh model
+    k.kernels[0].lengthscales.assign(1.7)
+    (f5, v5), n5 = launches(lambda: m.predict_f(Xs))
+    assert n5 == n_full
+    fresh = gp.models.GPR((X, Y), kernel=k, noise_variance=0.05)
+    f6, v6 = fresh.predict_f(Xs)
+    assert np.array_equal(np.asarray(f5), np.asarray(f6)) and np.array_equal(np.asarray(v5), np.asarray(v6))
+    assert not np.array_equal(np.asarray(f5), np.asarray(f1))
+    # mean function: the vectors are recomputed from the re-centred targets even when W is reused
+    mf = gp.mean_functions.Constant(0.3)
+    mm = gp.models.GPR((X, Y), kernel=k, noise_variance=0.05, mean_function=mf)
+    a1, _ = mm.predict_f(Xs)
+    mf.c.assign(np.array([-0.4]))
+    a2, _ = mm.predict_f(Xs)
+    ref = gp.models.GPR((X, Y), kernel=k, noise_variance=0.05, mean_function=gp.mean_functions.Constant(-0.4)).predict_f(Xs)[0]
+    np.testing.assert_allclose(np.asarray(a2), np.asarray(ref), rtol=1e-13, atol=1e-13)
+    assert not np.allclose(np.asarray(a1), np.asarray(a2))
