@@ -204,3 +204,35 @@ def test_svgp_minibatch_scaling_and_unwhitened():
     Lm = np.linalg.cholesky(O.K(k, Z) + O.DEFAULT_JITTER * np.eye(7))
     assert O.svgp_elbo(k, Z, Lm @ qm, (Lm @ qs[0])[None], 0.1, X, Y, whiten=False) == pytest.approx(
         O.svgp_elbo(k, Z, qm, qs, 0.1, X, Y), rel=1e-9)
+
+
+def test_sgpr_oracle_identities(monkeypatch):
+    """SGPR (gpflow/models/sgpr.py restatement): NumPy and torch versions agree; the collapsed bound is
+    below the exact LML and tight at Z = X; predict_f at Z = X is the exact GP posterior; the torch
+    gradient matches central differences."""
+    from oracle import gpflow_oracle_torch as T
+    monkeypatch.setattr(O, "DEFAULT_JITTER", 1e-11)
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(40, 2))
+    Y = np.sin(X[:, :1]) + 0.1 * rng.normal(size=(40, 1))
+    k = O.Sum([O.Leaf("se", variance=1.2, lengthscales=0.8), O.Leaf("matern32", variance=0.4, lengthscales=1.5)])
+    Z = X[:9].copy()
+    e_np = O.sgpr_elbo(k, Z, 0.1, X, Y)
+    e_t, g = T.sgpr_elbo_and_grad(k, Z, 0.1, X, Y)
+    assert e_np == pytest.approx(e_t, rel=1e-12)
+    lml = O.gpr_lml(k, X, Y, 0.1)
+    tight = O.sgpr_elbo(k, X, 0.1, X, Y)
+    assert e_np < lml and tight == pytest.approx(lml, rel=1e-8)
+    Xs = rng.normal(size=(7, 2))
+    fm, fv = O.sgpr_predict_f(k, X, 0.1, X, Y, Xs)
+    gm, gv = O.gpr_predict_f(k, X, Y, 0.1, Xs)
+    np.testing.assert_allclose(fm, gm, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(fv, gv, rtol=1e-6, atol=1e-9)
+    h = 1e-6
+    fd_noise = (O.sgpr_elbo(k, Z, 0.1 + h, X, Y) - O.sgpr_elbo(k, Z, 0.1 - h, X, Y)) / (2 * h)
+    assert g["noise"] == pytest.approx(fd_noise, rel=1e-6)
+    Zp, Zm = Z.copy(), Z.copy()
+    Zp[2, 1] += h
+    Zm[2, 1] -= h
+    fd_z = (O.sgpr_elbo(k, Zp, 0.1, X, Y) - O.sgpr_elbo(k, Zm, 0.1, X, Y)) / (2 * h)
+    assert g["Z"][2, 1] == pytest.approx(fd_z, rel=1e-5, abs=1e-7)
