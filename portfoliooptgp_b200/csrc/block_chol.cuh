@@ -181,96 +181,184 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
+    const int nt8 = np >> 3;
     if (tid == 0) *fail = 0;
-    for (int e = tid; e < (np >> 3) * 8 * DLD; e += nt) dinv[e] = 0.0;   // warp_diag_factor writes the lower parts only
+    for (int e = tid; e < nt8 * 8 * DLD; e += nt) dinv[e] = 0.0;   // warp_diag_factor writes the lower parts only
     __syncthreads();
-    if (warp == 0) warp_diag_factor(S, 0, fail, dinv);
-    __syncthreads();
-    GPB_POTRF_DECL
-    for (int p = 0; p + 8 < np; p += 8) {
+
+    // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores)
+    auto panel_tile = [&](int p, int ti) {
         const double* M = dinv + (p >> 3) * 8 * DLD;
-        const int mt = (np - p - 8) >> 3;
-        GPB_POTRF_STAMP(0)
-        // (b) panel tile <- tile * M^T  (in place: a warp's operand loads complete before its stores).
-        // With more than one warp, warp 0 owns the critical chain and never waits inside a step:
-        // panel tile 0 -> update of the next diagonal block -> its factorisation; it only ARRIVES at the
-        // named barrier that publishes panel tile 0 to the warps applying the rest of the update.
-        auto panel_tile = [&](int ti) {
-            double* Pt = S + (p + 8 + ti * 8) * SLD + p;
-            double c0 = 0.0, c1 = 0.0;
-            warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+        double* Pt = S + (p + 8 + ti * 8) * SLD + p;
+        double c0 = 0.0, c1 = 0.0;
+        warp_tile_mma(c0, c1, Pt, SLD, 1, M, 1, DLD, 8, 1.0);
+        __syncwarp();
+        *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
+    };
+
+    if (nwarps == 1) {
+        // single warp: plain right-looking loop
+        warp_diag_factor(S, 0, fail, dinv);
+        __syncwarp();
+        for (int p = 0; p + 8 < np; p += 8) {
+            const int mt = (np - p - 8) >> 3;
+            for (int ti = 0; ti < mt; ++ti) panel_tile(p, ti);
             __syncwarp();
-            *reinterpret_cast<double2*>(Pt + g * SLD + 2 * q) = make_double2(c0, c1);
-        };
-        if (nwarps > 1) {
-            if (warp == 0) {
-                panel_tile(0);
-                asm volatile("bar.arrive 1, %0;" ::"r"(nt) : "memory");
-                GPB_POTRF_STAMP(1)
-            } else {
-                for (int ti = warp; ti < mt; ti += nwarps - 1) panel_tile(ti);
-                GPB_POTRF_STAMP(1)
-                asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
-                GPB_POTRF_STAMP(2)
-            }
-        } else {
-            for (int ti = 0; ti < mt; ++ti) panel_tile(ti);
-            __syncwarp();
-        }
-        // (c) trailing update C -= P_ti P_tj^T over the 8x8 tiles (ti >= tj) of the trailing matrix, with
-        // look-ahead: warp 0 updates the next diagonal block (tile 0) and factors it at once, while the
-        // other warps apply the rest of the update.
-        const int ntiles = mt * (mt + 1) / 2;
-        if (nwarps > 1) {
-            if (warp == 0) {
-                __syncwarp();
-                warp_trailing_tile(S, p, 0);
-                __syncwarp();
-                GPB_POTRF_STAMP(2)
-                warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
-                GPB_POTRF_STAMP(3)
-            } else if ((warp & 3) != 0) {
-                // 16x16 super-tiles (I >= J) of the trailing tile grid, one per warp and round; tile (0,0)
-                // belongs to warp 0, tiles above the diagonal or past the edge are neither loaded nor stored.
-                // Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe (DMMA and DFMA issue to the same
-                // unit): they sit this phase out so that the pivot chain runs uncontended (measured:
-                // the in-situ diagonal factor was 35 % slower than the isolated one, tools/leaf_prof.cu).
-                const int o = p + 8, st = (mt + 1) >> 1, nst = st * (st + 1) / 2;
-                const int aw = warp - 1 - (warp >> 2), naw = nwarps - ((nwarps + 3) >> 2);
-                for (int t = aw; t < nst; t += naw) {
-                    int I, J;
-                    tri_tile(t, I, J);
-                    const int ti0 = 2 * I, tj0 = 2 * J;
-                    const bool a1 = ti0 + 1 < mt, b1 = (J < I) || a1;
-                    const bool v[2][2] = {{!(I == 0 && J == 0), J < I}, {a1, a1}};
-                    double c[2][2][2];
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rj = 0; rj < 2; ++rj) {
-                            double2 cc = make_double2(0.0, 0.0);
-                            if (v[ri][rj]) cc = *reinterpret_cast<const double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q);
-                            c[ri][rj][0] = cc.x;
-                            c[ri][rj][1] = cc.y;
-                        }
-                    warp_mma_2x2(c, S + (o + ti0 * 8) * SLD + p, SLD, 1, S + (o + tj0 * 8) * SLD + p, 1, SLD, 0, 8, -1.0, true,
-                                 a1, true, b1);
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rj = 0; rj < 2; ++rj)
-                            if (v[ri][rj])
-                                *reinterpret_cast<double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q) =
-                                    make_double2(c[ri][rj][0], c[ri][rj][1]);
-                }
-            }
-        } else {
-            for (int t = 0; t < ntiles; ++t) warp_trailing_tile(S, p, t);
+            for (int t = 0; t < mt * (mt + 1) / 2; ++t) warp_trailing_tile(S, p, t);
             __syncwarp();
             warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
+            __syncwarp();
         }
-        if (warp != 0) { GPB_POTRF_STAMP(3) }
-        __syncthreads();
+        return;
+    }
+
+    // Warp-specialised: two separate loops (their register live ranges do not mix), synchronised by named
+    // barriers: 1 publishes the panel tiles (warp 0 only ARRIVES, it never waits inside a step), 2 ends a step.
+    if (warp == 0) {
+        // the critical chain: panel tile 0 -> update of the next diagonal block -> its factorisation
+        warp_diag_factor(S, 0, fail, dinv);
+        asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
+        GPB_POTRF_DECL
+        for (int p = 0; p + 8 < np; p += 8) {
+            GPB_POTRF_STAMP(0)
+            panel_tile(p, 0);
+            asm volatile("bar.arrive 1, %0;" ::"r"(nt) : "memory");
+            GPB_POTRF_STAMP(1)
+            __syncwarp();
+            warp_trailing_tile(S, p, 0);
+            __syncwarp();
+            GPB_POTRF_STAMP(2)
+            warp_diag_factor(S, p + 8, fail, dinv + ((p + 8) >> 3) * 8 * DLD);
+            GPB_POTRF_STAMP(3)
+            asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
+            GPB_POTRF_STAMP(4)
+        }
+        return;
+    }
+
+    // Updating warps.  Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe (DMMA and DFMA issue to the same
+    // unit): they only help with the panel products and sit the update out, so that the pivot chain runs
+    // uncontended (measured: the in-situ diagonal factor was 35 % slower than the isolated one).
+    const int aw = warp - 1 - (warp >> 2), naw = nwarps - ((nwarps + 3) >> 2);   // index among the updating warps
+    const bool upd_warp = (warp & 3) != 0;
+    const int st_all = (nt8 + 1) >> 1, nst_all = st_all * (st_all + 1) / 2;
+    constexpr int OWN = 3;
+    // Trailing matrix in REGISTERS (12 or more updating warps): every updating warp owns up to three fixed
+    // 16x16 super-tiles (2x2 DMMA tiles) of the lower triangle for the whole factorisation and keeps their
+    // accumulators in registers across the panels; per panel it only reads the two panel fragments from
+    // shared memory.  A tile goes back to shared memory once, right after its last update: column-(k+1)
+    // tiles after panel k (they are the next panel), the diagonal tile (k+2, k+2) after panel k (warp 0
+    // applies its last update itself, in the look-ahead).  The C tiles were two thirds of the shared-memory
+    // traffic of the update, which bounded the first panels (tools/leaf_prof.cu).
+    const bool reg_path = nst_all <= OWN * naw;
+    int ownI[OWN], ownJ[OWN];
+    double acc[OWN][2][2][2];
+    if (reg_path && upd_warp) {
+#pragma unroll
+        for (int s_ = 0; s_ < OWN; ++s_) {
+            // u-th super-tile in the order J descending (longest-lived first), I ascending: dealt round robin
+            const int u = aw + s_ * naw;
+            int I = -1, J = -1;
+            if (u < nst_all) {
+                int base = 0;
+                for (int jj = st_all - 1; jj >= 0; --jj) {
+                    const int cnt = st_all - jj;
+                    if (u < base + cnt) { J = jj; I = jj + (u - base); break; }
+                    base += cnt;
+                }
+            }
+            ownI[s_] = I;
+            ownJ[s_] = J;
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                for (int rj = 0; rj < 2; ++rj) {
+                    const int ti = 2 * I + ri, tj = 2 * J + rj;
+                    // tiles this warp will ever update: column >= 1, on or below the diagonal, inside the matrix,
+                    // not the diagonal tiles (0,0), (1,1) (those only ever see warp 0)
+                    const bool mine = (I >= 0) && ti < nt8 && tj >= 1 && tj <= ti && !(ti == tj && tj <= 1);
+                    double2 cc = make_double2(0.0, 0.0);
+                    if (mine) cc = *reinterpret_cast<const double2*>(S + (ti * 8 + g) * SLD + tj * 8 + 2 * q);
+                    acc[s_][ri][rj][0] = cc.x;
+                    acc[s_][ri][rj][1] = cc.y;
+                }
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
+    GPB_POTRF_DECL
+    for (int p = 0; p + 8 < np; p += 8) {
+        const int mt = (np - p - 8) >> 3;
+        const int k = p >> 3;   // panel index
+        GPB_POTRF_STAMP(0)
+        for (int ti = warp; ti < mt; ti += nwarps - 1) panel_tile(p, ti);
+        GPB_POTRF_STAMP(1)
+        asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
+        GPB_POTRF_STAMP(2)
+        // (c) trailing update C -= P_ti P_tj^T over the 8x8 tiles (ti >= tj) right of the panel
+        if (upd_warp && reg_path) {
+#pragma unroll
+            for (int s_ = 0; s_ < OWN; ++s_) {
+                const int I = ownI[s_], J = ownJ[s_];
+                if (I < 0 || 2 * J + 1 <= k) continue;   // no tile of this super-tile is right of panel k any more
+                const int ti0 = 2 * I, tj0 = 2 * J;
+                bool act[2][2];
+#pragma unroll
+                for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                    for (int rj = 0; rj < 2; ++rj) {
+                        const int ti = ti0 + ri, tj = tj0 + rj;
+                        act[ri][rj] = tj > k && tj <= ti && ti < nt8 && !(ti == tj && tj == k + 1);
+                    }
+                const bool a0 = act[0][0] || act[0][1], a1 = act[1][0] || act[1][1];
+                const bool b0 = act[0][0] || act[1][0], b1 = act[0][1] || act[1][1];
+                if (a0 || a1)
+                    warp_mma_2x2(acc[s_], S + (ti0 * 8) * SLD + p, SLD, 1, S + (tj0 * 8) * SLD + p, 1, SLD, 0, 8, -1.0, a0, a1,
+                                 b0, b1);
+#pragma unroll
+                for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                    for (int rj = 0; rj < 2; ++rj) {
+                        const int ti = ti0 + ri, tj = tj0 + rj;
+                        const bool last = act[ri][rj] && ((ti != tj && tj == k + 1) || (ti == tj && tj == k + 2));
+                        if (last)
+                            *reinterpret_cast<double2*>(S + (ti * 8 + g) * SLD + tj * 8 + 2 * q) =
+                                make_double2(acc[s_][ri][rj][0], acc[s_][ri][rj][1]);
+                    }
+            }
+        } else if (upd_warp) {
+            // fewer updating warps than the register scheme needs: C tiles stay in shared memory; 16x16
+            // super-tiles (I >= J) of the trailing tile grid, one per warp and round; tile (0,0) belongs to
+            // warp 0, tiles above the diagonal or past the edge are neither loaded nor stored
+            const int o = p + 8, st = (mt + 1) >> 1, nst = st * (st + 1) / 2;
+            for (int t = aw; t < nst; t += naw) {
+                int I, J;
+                tri_tile(t, I, J);
+                const int ti0 = 2 * I, tj0 = 2 * J;
+                const bool a1 = ti0 + 1 < mt, b1 = (J < I) || a1;
+                const bool v[2][2] = {{!(I == 0 && J == 0), J < I}, {a1, a1}};
+                double c[2][2][2];
+#pragma unroll
+                for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                    for (int rj = 0; rj < 2; ++rj) {
+                        double2 cc = make_double2(0.0, 0.0);
+                        if (v[ri][rj]) cc = *reinterpret_cast<const double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q);
+                        c[ri][rj][0] = cc.x;
+                        c[ri][rj][1] = cc.y;
+                    }
+                warp_mma_2x2(c, S + (o + ti0 * 8) * SLD + p, SLD, 1, S + (o + tj0 * 8) * SLD + p, 1, SLD, 0, 8, -1.0, true, a1, true,
+                             b1);
+#pragma unroll
+                for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                    for (int rj = 0; rj < 2; ++rj)
+                        if (v[ri][rj])
+                            *reinterpret_cast<double2*>(S + (o + (ti0 + ri) * 8 + g) * SLD + o + (tj0 + rj) * 8 + 2 * q) =
+                                make_double2(c[ri][rj][0], c[ri][rj][1]);
+            }
+        }
+        GPB_POTRF_STAMP(3)
+        asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
         GPB_POTRF_STAMP(4)
     }
 }
