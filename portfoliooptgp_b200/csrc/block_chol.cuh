@@ -405,7 +405,10 @@ __device__ __forceinline__ void block_trtri_lower_inplace(double* S, int np, dou
         const int hb = bt >> 1, nsup = npairs * hb * hb;   // 16x16 super-tiles per phase
         // T_pr = L21 W11  (W11 lower: column tile tj needs k >= 8 tj only; its upper tiles hold garbage)
         for (int t = warp; t < nsup; t += nwarps) {
-            const int pr = t / (hb * hb), rem = t - pr * hb * hb, I = rem / hb, J = rem - I * hb;
+            // column super-tile rotated by (row, pair): the k-range of this phase shrinks with J, and warps
+            // w, w+4, w+8, w+12 share a scheduler (and its DMMA issue slot) -- without the rotation one
+            // scheduler would get all the J = 0 super-tiles (4x the products of the J = 3 ones)
+            const int pr = t / (hb * hb), rem = t - pr * hb * hb, I = rem / hb, J = (rem - I * hb + I + pr) % hb;
             const int r0 = pr * 2 * b, ti0 = 2 * I, tj0 = 2 * J;
             if (r0 + b + ti0 * 8 >= np) continue;                 // second block shorter than b (or absent)
             const bool a1 = r0 + b + (ti0 + 1) * 8 < np;
