@@ -32,7 +32,8 @@ def _kernels(gp, D):
     }
 
 
-@pytest.mark.parametrize("N,D", [(128, 8), (63, 7), (67, 3), (5, 1)])
+@pytest.mark.parametrize("N,D", [(128, 8), (63, 7), (67, 3), (5, 1), (1, 1), (8, 2), (9, 2), (17, 4), (33, 8), (96, 8), (104, 5),
+                                 (121, 16), (127, 8)])
 def test_batched_lml_grad_matches_oracle(gp, N, D):
     B = 6
     Xb, Yb = _windows(3, B, N, D)

@@ -39,7 +39,10 @@ def test_gemm_large_tiles():
     assert np.max(np.abs(dC.cpu().numpy() - A @ B.T)) < 1e-10
 
 
-@pytest.mark.parametrize("n", [5, 89, 128, 129, 300, 1000, 2500])
+# every leaf shape 1..128 rows that changes the tile grid of the in-shared-memory factorisation (1 to 16
+# panels, odd and even super-tile counts, ragged edges) plus multi-leaf sizes
+@pytest.mark.parametrize("n", [1, 2, 5, 7, 8, 9, 15, 16, 17, 24, 31, 32, 33, 40, 47, 48, 56, 63, 64, 65, 72, 80, 89, 96,
+                               104, 111, 112, 120, 121, 127, 128, 129, 200, 255, 256, 257, 300, 1000, 2500])
 def test_potrf_inv_lauum(n):
     import torch
     rng = np.random.default_rng(n)
