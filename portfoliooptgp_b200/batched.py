@@ -32,7 +32,7 @@ from .likelihoods import DEFAULT_VARIANCE_LOWER_BOUND
 
 def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]], X0: np.ndarray,
                     maxiter: int = 15000, maxfun: int = 15000, maxcor: int = 10, ftol: float = 2.2204460492503131e-09,
-                    gtol: float = 1e-5, maxls: int = 20) -> List[scipy.optimize.OptimizeResult]:
+                    gtol: float = 1e-5, maxls: int = 20, workers: int = 0) -> List[scipy.optimize.OptimizeResult]:
     """Minimise B independent problems with SciPy's L-BFGS-B, advancing them in lock step.
 
     ``fun_batch(X [b, n], idx [b]) -> (f [b], g [b, n])`` evaluates the problems ``idx`` at ``X``.
@@ -41,6 +41,8 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     f and g it is parked until every active problem has asked, then one ``fun_batch`` call serves
     them all."""
     from scipy.optimize import _lbfgsb_py as _lb
+    if workers and workers > 1 and len(X0) >= 4 * workers:
+        return _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, int(workers))
     _lbfgsb = _lb._lbfgsb
     int_dtype = np.int64 if getattr(_lb, "HAS_ILP64", False) else np.int32
     X0 = np.ascontiguousarray(X0, dtype=np.float64)
@@ -50,10 +52,11 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
 
     # State of all problems in 2-D arrays; setulb gets ROW VIEWS of them (contiguous), so that the only
     # per-problem Python work in a round is the setulb call itself and scattering / gathering x, f, g is
-    # vectorised.  Profile (5120 problems, n = 5): setulb takes ~13 us per call, two calls per problem
-    # and round, i.e. ~95 ms of host time per round against 2.5 ms on the device -- SciPy's own
-    # arithmetic is what bounds a full lock-step fit; it is kept because it reproduces scipy.optimize's
-    # iterates bit for bit.
+    # vectorised.  Profile (5120 problems, n = 5): with a multi-threaded BLAS setulb takes ~13 us per
+    # call (thread hand-off on 20 x 20 matrices), with one BLAS thread ~3 us -- hence the
+    # threadpool_limits(1) around the loop below (same arithmetic, same iterates).  SciPy's routine is kept
+    # because it reproduces scipy.optimize's iterates bit for bit; ``workers`` > 1
+    # spreads the calls over processes for another 2-3x.
     X = np.array(X0, dtype=np.float64)
     F = np.zeros((B,), dtype=np.float64)
     G = np.zeros((B, n), dtype=np.float64)
@@ -72,38 +75,46 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     args = [(m, X[b], low, up, nbd, F[b:b + 1].reshape(()), G[b], factr, gtol, WA[b], IWA[b], TASK[b], LSAVE[b], ISAVE[b],
              DSAVE[b], maxls, LN_TASK[b]) for b in range(B)]
     setulb = _lbfgsb.setulb
+    try:
+        from threadpoolctl import threadpool_limits
+        blas_single = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover - threadpoolctl ships with scikit-learn; the loop works without it
+        blas_single = None
 
-    active = list(range(B))
-    while active:
-        waiting = []
-        for b in active:
-            a = args[b]
-            task = a[11]
-            while True:  # advance until this problem needs f,g or stops
-                setulb(*a)
-                t0 = task[0]
-                if t0 == 3:
-                    waiting.append(b)
-                    break
-                elif t0 == 1:
-                    NIT[b] += 1
-                    if NIT[b] >= maxiter:
-                        task[0] = 5
-                        task[1] = 504
-                    elif NFEV[b] > maxfun:
-                        task[0] = 5
-                        task[1] = 502
-                else:
-                    break
-        if not waiting:
-            break
-        idx = np.asarray(waiting, dtype=np.int64)
-        fb, gb = fun_batch(X[idx], idx)
-        F[idx] = np.asarray(fb, dtype=np.float64)
-        G[idx] = np.asarray(gb, dtype=np.float64)
-        NFEV[idx] += 1
-        active = waiting
-
+    try:
+        active = list(range(B))
+        while active:
+            waiting = []
+            for b in active:
+                a = args[b]
+                task = a[11]
+                while True:  # advance until this problem needs f,g or stops
+                    setulb(*a)
+                    t0 = task[0]
+                    if t0 == 3:
+                        waiting.append(b)
+                        break
+                    elif t0 == 1:
+                        NIT[b] += 1
+                        if NIT[b] >= maxiter:
+                            task[0] = 5
+                            task[1] = 504
+                        elif NFEV[b] > maxfun:
+                            task[0] = 5
+                            task[1] = 502
+                    else:
+                        break
+            if not waiting:
+                break
+            idx = np.asarray(waiting, dtype=np.int64)
+            fb, gb = fun_batch(X[idx], idx)
+            F[idx] = np.asarray(fb, dtype=np.float64)
+            G[idx] = np.asarray(gb, dtype=np.float64)
+            NFEV[idx] += 1
+            active = waiting
+    finally:
+        if blas_single is not None:
+            blas_single.restore_original_limits()
     results = []
     for b in range(B):
         t0, t1 = int(TASK[b, 0]), int(TASK[b, 1])
@@ -117,6 +128,50 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
         msg = _lb.status_messages[t0] + ": " + _lb.task_messages[t1]
         results.append(scipy.optimize.OptimizeResult(fun=float(F[b]), jac=G[b].copy(), nfev=nfev, njev=nfev, nit=nit,
                                                      status=warnflag, message=msg, x=X[b].copy(), success=(warnflag == 0)))
+    return results
+
+
+def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, workers):
+    """lockstep_lbfgsb with the per-problem setulb calls spread over worker processes (_lbfgsb_pool):
+    the same call sequence per problem, so the same iterates; only the host time per round shrinks."""
+    from scipy.optimize import _lbfgsb_py as _lb
+    from . import _lbfgsb_pool
+    X0 = np.ascontiguousarray(X0, dtype=np.float64)
+    B, n = X0.shape
+    factr = ftol / np.finfo(float).eps
+    bounds = [(B * w) // workers for w in range(workers + 1)]
+    pool = _lbfgsb_pool.get_workers(workers)
+    for w, wk in enumerate(pool):
+        wk.send(("init", X0[bounds[w]:bounds[w + 1]], maxcor, factr, gtol, maxls, maxiter, maxfun))
+    replies = [wk.recv() for wk in pool]
+    while True:
+        counts = [len(r[0]) for r in replies]
+        if sum(counts) == 0:
+            break
+        idx = np.concatenate([r[0] + bounds[w] for w, r in enumerate(replies)])
+        Xb = np.concatenate([r[1] for r in replies], axis=0)
+        fb, gb = fun_batch(Xb, idx)
+        fb = np.asarray(fb, dtype=np.float64)
+        gb = np.asarray(gb, dtype=np.float64)
+        o = 0
+        for w, wk in enumerate(pool):
+            c = counts[w]
+            if c:
+                wk.send(("step", fb[o:o + c], gb[o:o + c]))
+            o += c
+        replies = [wk.recv() if counts[w] else replies[w] for w, wk in enumerate(pool)]
+    results = []
+    for wk in pool:
+        wk.send(("finish",))
+    for wk in pool:
+        X, F, G, TASK, NIT, NFEV = wk.recv()
+        for b in range(len(F)):
+            t0, t1 = int(TASK[b, 0]), int(TASK[b, 1])
+            nit, nfev = int(NIT[b]), int(NFEV[b])
+            warnflag = 0 if t0 == 4 else (1 if (nfev > maxfun or nit >= maxiter) else 2)
+            msg = _lb.status_messages[t0] + ": " + _lb.task_messages[t1]
+            results.append(scipy.optimize.OptimizeResult(fun=float(F[b]), jac=G[b].copy(), nfev=nfev, njev=nfev, nit=nit,
+                                                         status=warnflag, message=msg, x=X[b].copy(), success=(warnflag == 0)))
     return results
 
 
@@ -250,7 +305,8 @@ class BatchedGPR:
         return f, g
 
     def fit(self, maxiter: int = 15000, **lbfgs_kwargs) -> List[scipy.optimize.OptimizeResult]:
-        """Scipy().minimize(model.training_loss, model.trainable_variables) for every GP, lock step."""
+        """Scipy().minimize(model.training_loss, model.trainable_variables) for every GP, lock step.
+        ``workers=k`` (k > 1) advances the SciPy state machines in k worker processes (same iterates)."""
         U0 = self._pack()
         res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter, **lbfgs_kwargs)
         U = np.stack([r.x for r in res])

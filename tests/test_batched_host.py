@@ -84,3 +84,30 @@ def test_gather_results_gloo_world2():
     want = np.arange(11, dtype=np.float64)[:, None] * np.array([[1.0, 10.0, 100.0]])
     for _, full in outs:
         assert np.array_equal(full, want)
+
+
+def test_lockstep_workers_reproduce_the_in_process_iterates():
+    """workers > 1: slices of the batch advance in worker processes (_lbfgsb_pool); every result field is
+    bit-identical to the in-process driver (and therefore to scipy.optimize.minimize)."""
+    from portfoliooptgp_b200 import _lbfgsb_pool
+    from portfoliooptgp_b200.batched import lockstep_lbfgsb
+    B, n = 64, 4
+    rng = np.random.default_rng(5)
+    A = rng.uniform(0.5, 2.0, size=(B, n))
+    c = rng.normal(size=(B, n))
+
+    def fun(U, idx):
+        d = U - c[idx]
+        return 0.5 * np.sum(A[idx] * d * d, axis=1) + 0.1 * np.sum(d ** 4, axis=1) + np.sum(np.cos(d), axis=1), \
+            A[idx] * d + 0.4 * d ** 3 - np.sin(d)
+
+    X0 = rng.normal(size=(B, n))
+    r0 = lockstep_lbfgsb(fun, X0, maxiter=60)
+    try:
+        r1 = lockstep_lbfgsb(fun, X0, maxiter=60, workers=3)
+    finally:
+        _lbfgsb_pool.shutdown()
+    assert len(r1) == B
+    for a, b in zip(r0, r1):
+        assert np.array_equal(a.x, b.x) and a.fun == b.fun and np.array_equal(a.jac, b.jac)
+        assert (a.nit, a.nfev, a.status, a.message) == (b.nit, b.nfev, b.status, b.message)

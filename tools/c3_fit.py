@@ -21,9 +21,13 @@ def timed(U, idx):
     torch.cuda.synchronize(); dev_t[0] += time.perf_counter() - t0; calls[0] += 1
     return out
 m.loss_and_grads_unconstrained = timed
+workers = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if workers > 1:   # start the pool outside the timed region (interpreter + numpy/scipy import per worker)
+    from portfoliooptgp_b200 import _lbfgsb_pool
+    _lbfgsb_pool.get_workers(workers)
 t0 = time.perf_counter()
-res = m.fit(maxiter=100)
+res = m.fit(maxiter=100, workers=workers)
 dt = time.perf_counter() - t0
 nit = np.array([r.nit for r in res]); ok = np.array([r.success for r in res])
-print(f"C3 full fit: {B} GPs, {dt:.2f} s wall, {calls[0]} lock-step rounds, device+copies {dev_t[0]:.2f} s, host (SciPy setulb) {dt - dev_t[0]:.2f} s; "
+print(f"C3 full fit (workers={workers}): {B} GPs, {dt:.2f} s wall, {calls[0]} lock-step rounds, device+copies {dev_t[0]:.2f} s, host (SciPy setulb) {dt - dev_t[0]:.2f} s; "
       f"nit mean {nit.mean():.1f} max {nit.max()}, converged {ok.mean()*100:.1f} %, {B/dt:.0f} fits/s")
