@@ -90,14 +90,15 @@ __device__ __forceinline__ void warp_mma_2x2(double (&c)[2][2][2], const double*
 //   (a) warp 0 factors the 8x8 diagonal block and inverts the factor, entirely in registers
 //       (every lane redundantly: no shuffles on the pivot chain), stores L_pp and M = L_pp^-1;
 //   (b) panel  <- panel * M^T        one DMMA tile product per 8 rows;
-//   (c) trailing update C -= P P^T   DMMA tiles of the lower triangle, all warps.
+//   (c) trailing update C -= P P^T   DMMA tiles of the lower triangle, held in registers across panels.
+// Warp 0 owns the chain diagonal block -> panel tile 0 -> next diagonal block; the other warps run (b)
+// and (c) in a separate loop (block_potrf_lower below).
 // On exit the lower triangle holds L, the strict upper triangle of every 8x8 diagonal block is zero
 // (the rest of the upper triangle is never written), and dinv (shared, DINV_DOUBLES) holds the
 // inverses of the diagonal blocks (block b at dinv + b*8*DLD, row-major, stride DLD, zero upper).
 // *fail (shared int) = 1-based index of the first non-positive pivot, 0 if none; a failing pivot is
 // replaced by 1 so that no NaNs propagate.
-// (a) one warp, every lane redundantly: factor the 8x8 diagonal block at (p, p) in registers, invert the
-// factor, store L_pp (zero strict upper) and M = L_pp^-1.
+
 // 1/sqrt(d) for d > 0 in the normal range, branch-free: MUFU.RSQ64H seed (>= 20 bits) and one cubic
 // correction y (1 + e/2 + 3 e^2/8), e = 1 - d y^2  (|y^2 d - 1| <= 3e-16 measured, tools/lat_bench.cu;
 // 5 dependent FP64 ops, no slow-path call as in the library rsqrt).  d = +inf / NaN give NaN, which the
@@ -109,6 +110,8 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
     return fma(y, e * fma(0.375, e, 0.5), y);
 }
 
+// (a) one warp, every lane redundantly: factor the 8x8 diagonal block at (p, p) in registers, invert the
+// factor, store L_pp (zero strict upper) and M = L_pp^-1.
 __device__ __forceinline__ void warp_diag_factor(double* S, int p, int* fail, double* M) {
     // One straight-line block (a single warp runs it, so issue latency per instruction is what
     // counts): every lane holds the whole lower triangle in registers (broadcast LDS.128), the pivot
