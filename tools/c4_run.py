@@ -22,8 +22,13 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 lml = float(m.log_marginal_likelihood())
 torch.cuda.synchronize(); out["lml_s"] = time.perf_counter() - t0; out["lml"] = lml
 t0 = time.perf_counter()
-mean, var = m.predict_f(Xte)
+mean, var = m.predict_f(Xte)      # same theta as the LML evaluation above: the factorisation is reused
+torch.cuda.synchronize(); out["predict_f_after_lml_s"] = time.perf_counter() - t0
+m._fact = None                    # forget it: the stand-alone cost of predict_f (factorisation included)
+t0 = time.perf_counter()
+mean2, var2 = m.predict_f(Xte)
 torch.cuda.synchronize(); out["predict_f_s"] = time.perf_counter() - t0
+out["predict_reuse_identical"] = bool(torch.equal(mean, mean2) and torch.equal(var, var2))
 t0 = time.perf_counter()
 lml2, g, gn = m.lml_and_constrained_grads()
 torch.cuda.synchronize(); out["lml_grad_s"] = time.perf_counter() - t0
