@@ -68,15 +68,24 @@ static void factor_remember(gpb_handle* h, const double* theta, double noise) {
 
 // steps 1-3; leaves W, a, alpha, res[0..1], info on the device.  reuse: W and the log-det partials of the
 // previous call are still valid, only the vectors (which depend on the bound Y) are recomputed.
-static int gpr_factor(gpb_handle* h, const DevKernel& kp, double noise, GprWork& w, bool reuse = false) {
+static int gpr_factor_matrix(gpb_handle* h, const DevKernel& kp, double noise, GprWork& w) {
     int rc;
-    if (!reuse) {
-        if ((rc = launch_assemble(h, kp, h->d_X, h->N, h->d_X, h->N, h->D, w.A, w.ld, 1, noise))) return rc;
-        if ((rc = factor_inv(h, w.A, w.ld, w.W, w.ld, h->N, w.logdiag, w.info, false))) return rc;
-    }
+    if ((rc = launch_assemble(h, kp, h->d_X, h->N, h->d_X, h->N, h->D, w.A, w.ld, 1, noise))) return rc;
+    return factor_inv(h, w.A, w.ld, w.W, w.ld, h->N, w.logdiag, w.info, false);
+}
+
+// a = W y, alpha = W^T a, |a|^2 and the log-determinant: everything that depends on the bound targets
+static int gpr_factor_vectors(gpb_handle* h, GprWork& w) {
+    int rc;
     if ((rc = trmv_lower(h, w.W, w.ld, h->N, h->d_Yc, w.a))) return rc;
     if ((rc = trmv_lower_T(h, w.W, w.ld, h->N, w.a, w.alpha))) return rc;
     return quad_logdet(h, w.a, h->N, w.logdiag, w.res);
+}
+
+static int gpr_factor(gpb_handle* h, const DevKernel& kp, double noise, GprWork& w, bool reuse = false) {
+    int rc;
+    if (!reuse && (rc = gpr_factor_matrix(h, kp, noise, w))) return rc;
+    return gpr_factor_vectors(h, w);
 }
 
 int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, double* grad_theta, double* grad_noise,
@@ -90,12 +99,33 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
     if (kp.n_dims != h->D) return set_error(h, -2, "gpr: kernel expects D=%d, data has D=%d", kp.n_dims, h->D);
     GprWork w;
     if ((rc = gpr_workspaces(h, &w))) return rc;
-    if ((rc = gpr_factor(h, kp, noise, w))) return rc;
-    factor_remember(h, theta, noise);   // (a failed pivot invalidates it again below)
     const int P = kp.n_params;
-    if (want_grad) {
+    if (want_grad && h->fork_streams && h->side[0]) {
+        // the vector kernels (a, alpha, |a|^2, log-det) need W only, as does K^-1 = W^T W: they run on a side
+        // stream beside the big product and meet again in front of the gradient reduction (which needs both)
+        if ((rc = gpr_factor_matrix(h, kp, noise, w))) return rc;
+        cudaStream_t main_stream = h->stream, side = h->side[0];
+        cudaError_t e = cudaEventRecord(h->ev_fork[0], main_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, h->ev_fork[0], 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "gpr fork");
+        h->stream = side;
+        rc = gpr_factor_vectors(h, w);
+        h->stream = main_stream;
+        if (rc) return rc;
+        e = cudaEventRecord(h->ev_join[0], side);
+        if (e != cudaSuccess) return check_cuda(h, e, "gpr join record");
         if ((rc = lauum_lower(h, w.W, h->N, w.ld, w.A, w.ld))) return rc;
+        e = cudaStreamWaitEvent(main_stream, h->ev_join[0], 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "gpr join");
+        factor_remember(h, theta, noise);   // (a failed pivot invalidates it again below)
         if ((rc = launch_grad_reduce(h, kp, h->d_X, h->N, h->D, w.A, w.ld, w.alpha, w.res + 2))) return rc;
+    } else {
+        if ((rc = gpr_factor(h, kp, noise, w))) return rc;
+        factor_remember(h, theta, noise);   // (a failed pivot invalidates it again below)
+        if (want_grad) {
+            if ((rc = lauum_lower(h, w.W, h->N, w.ld, w.A, w.ld))) return rc;
+            if ((rc = launch_grad_reduce(h, kp, h->d_X, h->N, h->D, w.A, w.ld, w.alpha, w.res + 2))) return rc;
+        }
     }
     // one D2H of [quad, logdet, g_0..g_P] + info, then the only sync of the evaluation
     double* hp = pinned(h, (size_t)(64 + 2) * sizeof(double));
