@@ -231,3 +231,21 @@ def test_predict_reuses_the_factorisation_only_when_it_may(gp):
     ref = gp.models.GPR((X, Y), kernel=k, noise_variance=0.05, mean_function=gp.mean_functions.Constant(-0.4)).predict_f(Xs)[0]
     np.testing.assert_allclose(np.asarray(a2), np.asarray(ref), rtol=1e-13, atol=1e-13)
     assert not np.allclose(np.asarray(a1), np.asarray(a2))
+
+
+def test_evaluations_are_bitwise_reproducible(gp):
+    """Fixed-order reductions, no atomics on values: repeated evaluations (side streams, PDL, the batched
+    kernel's warp-specialised Cholesky) return identical bits."""
+    X, Y = make_multi_input(3, 600, 8)
+    k = gp.kernels.SquaredExponential() + gp.kernels.Matern52() + gp.kernels.Linear()
+    m = gp.models.GPR((X, Y), kernel=k, noise_variance=1e-2)
+    ref = m.lml_and_constrained_grads()
+    for _ in range(40):
+        out = m.lml_and_constrained_grads()
+        assert out[0] == ref[0] and np.array_equal(out[1], ref[1]) and out[2] == ref[2]
+    Xb = np.stack([X[i:i + 128] for i in range(40)])
+    Yb = np.stack([Y[i:i + 128, 0] for i in range(40)])
+    b = gp.BatchedGPR(Xb, Yb, k, noise_variance=0.1)
+    r0 = b.lml_and_grads()
+    for _ in range(20):
+        assert all(np.array_equal(a, c) for a, c in zip(b.lml_and_grads(), r0))
