@@ -45,6 +45,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
                   int N, int D, int mode, double* __restrict__ out, int* __restrict__ info,
                   const double* __restrict__ Xs_new, int Ns, double* __restrict__ mean_out,
                   double* __restrict__ var_out, long long* __restrict__ prof) {
+    using SHE = UnitWeights<SH>;   // element routines: the per-GP descriptor is in global memory
     extern __shared__ __align__(16) double sm[];
     double* S = sm + BatchedSmem::S;
     double* T = sm + BatchedSmem::T;
@@ -99,7 +100,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
             }
             double v[4];
             if (fastk) {
-                kernel_value_2x2<DP, SH>(kp, xa, xb, xj0, xj1, v);
+                kernel_value_2x2<DP, SHE>(kp, xa, xb, xj0, xj1, v);
             } else {
                 v[0] = kernel_value<DP>(kp, xa, xj0);
                 v[1] = kernel_value<DP>(kp, xa, xj1);
@@ -169,7 +170,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
                 double xi[DP];
 #pragma unroll
                 for (int d = 0; d < DP; ++d) xi[d] = xs[i * XSTR + d];
-                const double kv = (i < N) ? kernel_value_auto<DP, SH>(kp, xi, xn) : 0.0;
+                const double kv = (i < N) ? kernel_value_auto<DP, SHE>(kp, xi, xn) : 0.0;
                 ks[warp * 128 + i] = kv;
                 m = fma(kv, als[i], m);
             }
@@ -186,7 +187,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
             for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
             if (lane == 0) {
                 mean_out[(size_t)b * Ns + s0] = m;
-                var_out[(size_t)b * Ns + s0] = (SH::is_static ? kernel_value_fast<DP, SH>(kp, xn, xn) : kernel_value<DP>(kp, xn, xn)) - ss;
+                var_out[(size_t)b * Ns + s0] = (SH::is_static ? kernel_value_fast<DP, SHE>(kp, xn, xn) : kernel_value<DP>(kp, xn, xn)) - ss;
             }
             __syncwarp();
         }
@@ -225,7 +226,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
                             if (j == i) tr += w; else w *= 2.0;
 #pragma unroll
                             for (int d = 0; d < DP; ++d) xj[d] = xs[j * XSTR + d];
-                            if (fast) kernel_value_grad_fast<DP, SH>(kp, xi, xj, w, A);
+                            if (fast) kernel_value_grad_fast<DP, SHE>(kp, xi, xj, w, A);
                             else kernel_value_grad<DP>(kp, xi, xj, w, acc);
                         }
                     }

@@ -93,7 +93,7 @@ struct DevGroup {
     int kind;
     int ard_index;     // theta index of first ARD lengthscale, or -1
     int period_index;  // theta index of period, or -1
-    int pad_;
+    unsigned dim_mask; // active dimensions (bit d); with no ARD lengthscales the weights are exactly this mask
     double inv_period;
     double w[GPB_MAX_DIMS];       // per-dim weight: mask (0/1) or ARD 1/l_d^2 (or 1/l_d for PERIODIC_ABS)
     double inv_ls[GPB_MAX_DIMS];  // ARD only: 1/l_d (for the lengthscale derivative)
@@ -137,6 +137,7 @@ struct DynShape {
     static constexpr bool is_static = false;
     static constexpr int HAS_KINK = 0;   // unused: the interpreter gets it as a kernel argument
     static constexpr bool FUSED2 = false;
+    static constexpr bool UNIT_W = false;
     static __host__ __device__ __forceinline__ int n_groups(const DevKernel& kp) { return kp.n_groups; }
     static __host__ __device__ __forceinline__ int group_kind(const DevKernel& kp, int g) { return kp.groups[g].kind; }
     static __host__ __device__ __forceinline__ int n_leaves(const DevKernel& kp) { return kp.n_leaves; }
@@ -154,6 +155,7 @@ struct DynShape {
 template <int G0, int G1, int L0, int L1, int L2, int L3, int T0, int T1, int T2, int T3>
 struct StaticShape {
     static constexpr bool is_static = true;
+    static constexpr bool UNIT_W = false;   // see UnitWeights below
     static constexpr int NG = (G0 >= 0) + (G1 >= 0);
     static constexpr int NL = (L0 >= 0) + (L1 >= 0) + (L2 >= 0) + (L3 >= 0);
     static constexpr int NT = (T0 != 0) + (T1 != 0) + (T2 != 0) + (T3 != 0);
@@ -186,6 +188,16 @@ struct StaticShape {
     static __host__ __device__ constexpr int term_leaf(const DevKernel&, int t, int f) { return (tcode(t) >> (4 + 4 * f)) & 15; }
 };
 
+// A straight-line shape has no per-dimension lengthscales, so a group's weights are its 0/1 active-dimension
+// mask.  Kernels whose descriptor lives in GLOBAL memory (one per GP in the batched kernel) or that are short
+// of FP64 issue slots read one mask word and predicate the dimensions instead of loading and multiplying a
+// weight per dimension; kernels that get the descriptor as a __grid_constant__ parameter keep the weights
+// (there they are free constant-bank operands and the predicates only cost: grad_reduce 0.43 -> 0.46 ms).
+template <class SH>
+struct UnitWeights : SH {
+    static constexpr bool UNIT_W = SH::is_static;
+};
+
 // does the descriptor have exactly the structure SH encodes (and no per-dimension lengthscales)?
 template <class SH>
 inline bool shape_matches(const DevKernel& kp) {
@@ -212,7 +224,8 @@ __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, c
     for (int g = 0; g < s.n_groups; ++g) {
         const gpb_group& G = s.groups[g];
         DevGroup& d = out->groups[g];
-        d.kind = G.kind; d.ard_index = G.ard_index; d.period_index = G.period_index; d.pad_ = 0;
+        d.kind = G.kind; d.ard_index = G.ard_index; d.period_index = G.period_index;
+        d.dim_mask = (s.n_dims >= 32) ? G.dim_mask : (G.dim_mask & ((1u << s.n_dims) - 1u));
         d.inv_period = (G.period_index >= 0) ? 1.0 / theta[G.period_index] : 0.0;
         int k = 0;
         for (int dim = 0; dim < GPB_MAX_DIMS; ++dim) {
@@ -259,22 +272,43 @@ __host__ __device__ inline int build_dev_kernel_core(const gpb_kernel_spec& s, c
 
 // ---- group value -------------------------------------------------------------------------------
 // s = reduction over active dims; when GRAD also returns ds/dperiod.
-template <int DP, bool GRAD>
+// UNIT: the group has no per-dimension lengthscales (guaranteed for the straight-line shapes), so its weights
+// are the 0/1 active-dimension mask: one mask word and predicated dimensions instead of a weight load and a
+// multiply per dimension.
+template <int DP, bool GRAD, bool UNIT = false>
 __device__ __forceinline__ double group_value_k(const DevGroup& g, int kind, const double (&xi)[DP],
                                                 const double (&xj)[DP], double& ds_dperiod) {
     double s = 0.0;
     if (GRAD) ds_dperiod = 0.0;
     switch (kind) {
         case GPB_GROUP_EUCLID: {
+            if (UNIT) {
+                const unsigned mk = g.dim_mask;
 #pragma unroll
-            for (int d = 0; d < DP; ++d) {
-                double t = xi[d] - xj[d];
-                s = fma(g.w[d] * t, t, s);
+                for (int d = 0; d < DP; ++d) {
+                    if ((mk >> d) & 1u) {
+                        const double t = xi[d] - xj[d];
+                        s = fma(t, t, s);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; ++d) {
+                    double t = xi[d] - xj[d];
+                    s = fma(g.w[d] * t, t, s);
+                }
             }
         } break;
         case GPB_GROUP_DOT: {
+            if (UNIT) {
+                const unsigned mk = g.dim_mask;
 #pragma unroll
-            for (int d = 0; d < DP; ++d) s = fma(g.w[d] * xi[d], xj[d], s);
+                for (int d = 0; d < DP; ++d)
+                    if ((mk >> d) & 1u) s = fma(xi[d], xj[d], s);
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; ++d) s = fma(g.w[d] * xi[d], xj[d], s);
+            }
         } break;
         case GPB_GROUP_PERIODIC_SQ: {
 #pragma unroll
@@ -536,7 +570,7 @@ __device__ __forceinline__ double kernel_value_fast(const DevKernel& kp, const d
             const int gi = SH::leaf_group(kp, l);
             if (gi != g_prev) {
                 double dummy;
-                s_prev = group_value_k<DP, false>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dummy);
+                s_prev = group_value_k<DP, false, SH::UNIT_W>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dummy);
                 g_prev = gi;
             }
             v[l] = leaf_value_k<false>(lf, SH::leaf_kind(kp, l), SH::leaf_arg_is_r(kp, l), s_prev).v;
@@ -621,10 +655,10 @@ __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const doub
             if (gi != g_prev) {
                 double dummy;
                 const DevGroup& g = kp.groups[gi];
-                s[0] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xa, xj0, dummy);
-                s[1] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xa, xj1, dummy);
-                s[2] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xb, xj0, dummy);
-                s[3] = group_value_k<DP, false>(g, GPB_GROUP_EUCLID, xb, xj1, dummy);
+                s[0] = group_value_k<DP, false, SH::UNIT_W>(g, GPB_GROUP_EUCLID, xa, xj0, dummy);
+                s[1] = group_value_k<DP, false, SH::UNIT_W>(g, GPB_GROUP_EUCLID, xa, xj1, dummy);
+                s[2] = group_value_k<DP, false, SH::UNIT_W>(g, GPB_GROUP_EUCLID, xb, xj0, dummy);
+                s[3] = group_value_k<DP, false, SH::UNIT_W>(g, GPB_GROUP_EUCLID, xb, xj1, dummy);
                 g_prev = gi;
             }
 #pragma unroll
@@ -653,10 +687,10 @@ __device__ __forceinline__ void kernel_value_2x2(const DevKernel& kp, const doub
                 double dummy;
                 const DevGroup& g = kp.groups[gi];
                 const int gk = SH::group_kind(kp, gi);
-                s[0] = group_value_k<DP, false>(g, gk, xa, xj0, dummy);
-                s[1] = group_value_k<DP, false>(g, gk, xa, xj1, dummy);
-                s[2] = group_value_k<DP, false>(g, gk, xb, xj0, dummy);
-                s[3] = group_value_k<DP, false>(g, gk, xb, xj1, dummy);
+                s[0] = group_value_k<DP, false, SH::UNIT_W>(g, gk, xa, xj0, dummy);
+                s[1] = group_value_k<DP, false, SH::UNIT_W>(g, gk, xa, xj1, dummy);
+                s[2] = group_value_k<DP, false, SH::UNIT_W>(g, gk, xb, xj0, dummy);
+                s[3] = group_value_k<DP, false, SH::UNIT_W>(g, gk, xb, xj1, dummy);
                 g_prev = gi;
             }
             leaf_value_vec_k<4>(lf, SH::leaf_kind(kp, l), SH::leaf_arg_is_r(kp, l), s, v[l]);
@@ -699,7 +733,7 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
             const int gi = SH::leaf_group(kp, l);
             if (gi != g_prev) {
                 double dummy;
-                s_prev = group_value_k<DP, false>(kp.groups[gi], GPB_GROUP_EUCLID, xi, xj, dummy);
+                s_prev = group_value_k<DP, false, SH::UNIT_W>(kp.groups[gi], GPB_GROUP_EUCLID, xi, xj, dummy);
                 g_prev = gi;
             }
             arg += pure_exp_arg<true>(kp.leaves[l], SH::leaf_kind(kp, l), s_prev, dl[l]);
@@ -724,7 +758,7 @@ __device__ __forceinline__ double kernel_value_grad_fast(const DevKernel& kp, co
             const DevLeaf& lf = kp.leaves[l];
             const int gi = SH::leaf_group(kp, l), air = SH::leaf_arg_is_r(kp, l);
             if (gi != g_prev) {
-                s_prev = group_value_k<DP, true>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
+                s_prev = group_value_k<DP, true, SH::UNIT_W>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
                 g_prev = gi;
             }
             const LeafOut lo = leaf_value_k<true>(lf, SH::leaf_kind(kp, l), air, s_prev);
@@ -844,7 +878,7 @@ __device__ __forceinline__ double kernel_value_grad_x_fast(const DevKernel& kp, 
             const DevLeaf& lf = kp.leaves[l];
             const int gi = SH::leaf_group(kp, l), air = SH::leaf_arg_is_r(kp, l);
             if (gi != g_prev) {
-                s_prev = group_value_k<DP, true>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
+                s_prev = group_value_k<DP, true, SH::UNIT_W>(kp.groups[gi], SH::group_kind(kp, gi), xi, xj, dsp_prev);
                 g_prev = gi;
             }
             const LeafOut lo = leaf_value_k<true>(lf, SH::leaf_kind(kp, l), air, s_prev);

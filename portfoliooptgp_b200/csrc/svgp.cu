@@ -83,7 +83,7 @@ cross_grad_kernel(const __grid_constant__ DevKernel kp, const double* __restrict
 #pragma unroll
                 for (int d = 0; d < DP; ++d) xj[d] = xb[cc][d];
                 const double w = wst[r * (CG_TILE + 1) + cc];
-                kernel_value_grad_x_fast<DP, SH>(kp, xi, xj, w, A, gx);
+                kernel_value_grad_x_fast<DP, UnitWeights<SH>>(kp, xi, xj, w, A, gx);
             }
         }
     }
