@@ -123,8 +123,12 @@ def direct_square_distance(X, X2=None):
     """Direct-difference form sum_d (x_d - x'_d)^2 (what the fused CUDA kernel evaluates);
     mathematically identical to square_distance, used to quantify the Gram-form rounding gap."""
     X2 = X if X2 is None else X2
-    d = X[:, None, :] - X2[None, :, :]
-    return np.sum(d * d, axis=-1)
+    out = np.zeros((X.shape[0], X2.shape[0]), dtype=np.float64)
+    for j in range(X.shape[1]):      # one dimension at a time: O(N N2) memory at the BASELINE sizes
+        d = X[:, j][:, None] - X2[:, j][None, :]
+        d *= d
+        out += d
+    return out
 
 
 _DISTANCE_FORM = "gram"  # "gram" = GPflow-faithful; tests flip to "direct" to bound the gap

@@ -150,13 +150,6 @@ int build_dev_kernel(gpb_handle* h, const double* theta, DevKernel* out) {
 
 using namespace gpb;
 
-#define GPB_ENTER(h)                          \
-    if (!(h)) return -1;                      \
-    {                                         \
-        cudaError_t e_ = cudaSetDevice((h)->device); \
-        if (e_ != cudaSuccess) return check_cuda((h), e_, "cudaSetDevice"); \
-    }
-
 extern "C" {
 
 int gpb_version(void) { return 100; }
@@ -168,7 +161,8 @@ int gpb_create(gpb_handle** out, int device) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) return -10;  // no CUDA device: there is no CPU fallback
     if (device < 0 || device >= count) return -2;
-    if (cudaSetDevice(device) != cudaSuccess) return -11;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return -11;
     gpb_handle* h = new (std::nothrow) gpb_handle();
     if (!h) return -12;
     h->device = device;
@@ -191,7 +185,7 @@ int gpb_create(gpb_handle** out, int device) {
 
 int gpb_destroy(gpb_handle* h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 8; ++i)
         if (h->buf[i]) cudaFree(h->buf[i]);

@@ -94,6 +94,29 @@ struct ProfScope {
 
 int set_error(gpb_handle* h, int code, const char* fmt, ...);
 int check_cuda(gpb_handle* h, cudaError_t e, const char* what);
+
+// Every C-ABI entry point runs on the handle's device and puts the caller's current device back on
+// return (the caller -- torch -- reads it through cudaGetDevice; a process may hold engines on several
+// GPUs).  One macro for all translation units: GPB_ENTER(h) declares the guard and returns on failure.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) { prev = -1; return; }
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GPB_ENTER(h)                                                                     \
+    if (!(h)) return -1;                                                                 \
+    gpb::DeviceGuard gpb_device_guard_((h)->device);                                     \
+    if (gpb_device_guard_.err != cudaSuccess) return gpb::check_cuda((h), gpb_device_guard_.err, "cudaSetDevice")
 // returns nullptr (and sets error) on failure
 double* workspace(gpb_handle* h, int id, size_t bytes);
 double* pinned(gpb_handle* h, size_t bytes);

@@ -223,9 +223,7 @@ int gpr_get_alpha(gpb_handle* h, double* d_alpha) {
 }  // namespace gpb
 
 extern "C" int gpb_gpr_get_alpha(gpb_handle* h, double* d_alpha) {
-    if (!h) return -1;
-    cudaError_t e_ = cudaSetDevice(h->device);
-    if (e_ != cudaSuccess) return gpb::check_cuda(h, e_, "cudaSetDevice");
+    GPB_ENTER(h);
     if (!d_alpha) return gpb::set_error(h, -2, "get_alpha: null pointer");
     return gpb::gpr_get_alpha(h, d_alpha);
 }

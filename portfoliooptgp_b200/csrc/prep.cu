@@ -185,18 +185,11 @@ int prep_windows(gpb_handle* h, const double* d_feat, const double* d_y, int64_t
 
 }  // namespace gpb
 
-#define GPB_PREP_ENTER(h)                                                          \
-    if (!(h)) return -1;                                                           \
-    {                                                                              \
-        cudaError_t e_ = cudaSetDevice((h)->device);                               \
-        if (e_ != cudaSuccess) return gpb::check_cuda((h), e_, "cudaSetDevice");   \
-    }
-
 extern "C" {
 
 int gpb_prep_returns(gpb_handle* h, const double* d_close, const double* d_open, int64_t T, int64_t A, int kind,
                      double* d_out) {
-    GPB_PREP_ENTER(h);
+    GPB_ENTER(h);
     if (T < 0 || A < 0) return gpb::set_error(h, -2, "prep_returns: negative size");
     if (kind < 0 || kind > 2) return gpb::set_error(h, -2, "prep_returns: kind %d not in {0,1,2}", kind);
     if (T * A > 0 && (!d_close || !d_out)) return gpb::set_error(h, -2, "prep_returns: null pointer");
@@ -206,7 +199,7 @@ int gpb_prep_returns(gpb_handle* h, const double* d_close, const double* d_open,
 
 int gpb_prep_zscore(gpb_handle* h, const double* d_x, int64_t T, int64_t A, int ddof, double* d_out, int64_t ldo,
                     double* d_mean, double* d_std) {
-    GPB_PREP_ENTER(h);
+    GPB_ENTER(h);
     if (T < 0 || A < 0) return gpb::set_error(h, -2, "prep_zscore: negative size");
     if (ddof < 0 || ddof > 1) return gpb::set_error(h, -2, "prep_zscore: ddof must be 0 or 1");
     if (T * A > 0 && !d_x) return gpb::set_error(h, -2, "prep_zscore: null pointer");
@@ -216,7 +209,7 @@ int gpb_prep_zscore(gpb_handle* h, const double* d_x, int64_t T, int64_t A, int 
 
 int gpb_prep_windows(gpb_handle* h, const double* d_feat, const double* d_y, int64_t S, int64_t T, int D, int64_t N,
                      int64_t stride, double* d_X, double* d_Y) {
-    GPB_PREP_ENTER(h);
+    GPB_ENTER(h);
     if (S < 0 || T < 0 || D < 1 || N < 1 || stride < 1) return gpb::set_error(h, -2, "prep_windows: bad sizes");
     if (S == 0 || T < N) return 0;  // no complete window
     if (!d_feat || !d_X) return gpb::set_error(h, -2, "prep_windows: null pointer");

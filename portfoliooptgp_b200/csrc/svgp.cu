@@ -976,9 +976,7 @@ int adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double
 
 extern "C" int gpb_adam_step(gpb_handle* h, double* d_x, const double* d_g, double* d_m, double* d_v, int64_t n, double lr,
                              double beta1, double beta2, double eps, int64_t step, int maximize) {
-    if (!h) return -1;
-    cudaError_t e_ = cudaSetDevice(h->device);
-    if (e_ != cudaSuccess) return gpb::check_cuda(h, e_, "cudaSetDevice");
+    GPB_ENTER(h);
     if (!d_x || !d_g || !d_m || !d_v || step < 1) return gpb::set_error(h, -2, "adam_step: bad arguments");
     return gpb::adam_step(h, d_x, d_g, d_m, d_v, n, lr, beta1, beta2, eps, step, maximize ? 1.0 : -1.0);
 }

@@ -56,6 +56,32 @@ def make_multi_input(seed, n, d):
     return np.ascontiguousarray(X), np.ascontiguousarray(y)
 
 
+def make_c1(n=1000, seed=1):
+    """SURVEY.md 8d C1 (BASELINE config 1): z-scored day index, z-scored synthetic daily returns with a
+    21-day cycle; the same generator as bench.py::make_c1 and tests/golden/make_truth.py::make_c1."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64)[:, None]
+    X = (t - t.mean()) / t.std()
+    r = rng.normal(0, 0.01, size=(n, 1)) + 0.004 * np.sin(2 * np.pi * t / 21.0)
+    Y = (r - r.mean()) / r.std()
+    return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def record_parity(name, payload):
+    """Append one measured-parity record to gpurun_out/parity_measured.jsonl (travels back from the GPU
+    box; the numbers quoted in DESIGN.md section 10 come from this file)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, **payload}) + "\n")
+    except OSError:
+        pass
+
+
 def kernel_zoo(D):
     """Kernel expressions covering the reference call sites and every leaf/group kind."""
     K = gpflow.kernels

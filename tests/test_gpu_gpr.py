@@ -178,6 +178,9 @@ def test_two_devices_in_one_process(gp):
         bg = gp.BatchedGPR(np.stack([X[i:i + 128] for i in range(4)]), np.stack([Y[i:i + 128, 0] for i in range(4)]), k,
                            noise_variance=0.1, device=dev)
         out.append((lml, g, gn, np.asarray(fm), np.asarray(fv), bg.lml_and_grads()[0]))
+        # the C-ABI restores the caller's current device on return (a call on a cuda:1 model must
+        # not move torch's current device)
+        assert torch.cuda.current_device() == 0, dev
     assert out[0][0] == out[1][0] and out[0][2] == out[1][2]
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4])
     assert np.array_equal(out[0][5], out[1][5])

@@ -95,13 +95,24 @@ __global__ void k_m16n8k16(double* out, int iters, double a, double b) {
 template <typename F>
 static float time_it(F launch) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    launch(); launch(); cudaDeviceSynchronize();
+    // a launch that fails (e.g. 1024 threads of a kernel that needs > 64 registers each) must not be
+    // printed as a measurement: every launch and the final sync are checked, failure returns a negative time
+    launch(); launch();
+    if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1.f; }
     float best = 1e30f;
     for (int r = 0; r < 5; ++r) {
-        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); launch();
+        if (cudaGetLastError() != cudaSuccess) return -1.f;
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     return best;
+}
+
+static void report(const char* what, int warps, float ms, double flop) {
+    if (ms <= 0.f) printf("%s warps/cta %2d: LAUNCH FAILED (not a measurement)\n", what, warps);
+    else printf("%s warps/cta %2d: %.2f TFLOP/s\n", what, warps, flop / ms / 1e9);
 }
 
 int main() {
@@ -114,16 +125,16 @@ int main() {
         int threads = warps * 32; int blocks = sms * 2;
         double nthr = (double)blocks * threads;
         float ms = time_it([&] { k_dfma<16><<<blocks, threads>>>(out, iters, 1.000001, 1e-9); });
-        printf("dfma ilp16 warps/cta %2d (2 cta/sm): %.2f TFLOP/s\n", warps, 2.0 * 16 * iters * nthr / ms / 1e9);
+        report("dfma ilp16 (2 cta/sm)", warps, ms, 2.0 * 16 * iters * nthr);
         double nwarp = (double)blocks * warps;
         ms = time_it([&] { k_m8n8k4<16><<<blocks, threads>>>(out, iters, 1.000001, 1e-9); });
-        printf("dmma m8n8k4   warps/cta %2d: %.2f TFLOP/s\n", warps, 2.0 * 8 * 8 * 4 * 16 * iters * nwarp / ms / 1e9);
+        report("dmma m8n8k4  ", warps, ms, 2.0 * 8 * 8 * 4 * 16 * iters * nwarp);
         ms = time_it([&] { k_m16n8k4<8><<<blocks, threads>>>(out, iters, 1.000001, 1e-9); });
-        printf("dmma m16n8k4  warps/cta %2d: %.2f TFLOP/s\n", warps, 2.0 * 16 * 8 * 4 * 8 * iters * nwarp / ms / 1e9);
+        report("dmma m16n8k4 ", warps, ms, 2.0 * 16 * 8 * 4 * 8 * iters * nwarp);
         ms = time_it([&] { k_m16n8k8<8><<<blocks, threads>>>(out, iters, 1.000001, 1e-9); });
-        printf("dmma m16n8k8  warps/cta %2d: %.2f TFLOP/s\n", warps, 2.0 * 16 * 8 * 8 * 8 * iters * nwarp / ms / 1e9);
+        report("dmma m16n8k8 ", warps, ms, 2.0 * 16 * 8 * 8 * 8 * iters * nwarp);
         ms = time_it([&] { k_m16n8k16<8><<<blocks, threads>>>(out, iters, 1.000001, 1e-9); });
-        printf("dmma m16n8k16 warps/cta %2d: %.2f TFLOP/s\n", warps, 2.0 * 16 * 8 * 16 * 8 * iters * nwarp / ms / 1e9);
+        report("dmma m16n8k16", warps, ms, 2.0 * 16 * 8 * 16 * 8 * iters * nwarp);
     }
     cudaFree(out);
     return 0;
