@@ -25,6 +25,14 @@ import sys
 import threading
 import time
 
+# The CPU legs (--impl reference, cpu_baseline) must use every host core even under torchrun, which exports
+# OMP_NUM_THREADS=1 to its workers (the reference arm halved at N >= 2).  The BLAS /
+# OpenMP pools read these variables when the libraries load, so they are set before numpy is imported;
+# cpu_threads() pins the pools again at run time through threadpoolctl.
+if "reference" in sys.argv[1:] or any(a.startswith("--impl=reference") for a in sys.argv[1:]):
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -125,13 +133,28 @@ def cpu_lml_grad_once(X, Y):
     return time.perf_counter() - t0, out
 
 
+_POOL_LIMIT = None
+
+
 def cpu_threads():
+    """Pin every BLAS / OpenMP pool in the process to all host cores (threadpoolctl changes the live
+    pools, whatever OMP_NUM_THREADS said at load time) and return the LAPACK/BLAS thread count actually
+    in force -- the `cores` the CPU legs report."""
+    global _POOL_LIMIT
+    n = os.cpu_count() or 1
     try:
         import torch
-        n = os.cpu_count() or 1
         torch.set_num_threads(n)
     except Exception:
-        n = os.cpu_count() or 1
+        pass
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        _POOL_LIMIT = threadpool_limits(limits=n)     # kept alive: the limit holds for the rest of the run
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            n = max(blas)
+    except Exception:
+        pass
     return n
 
 

@@ -103,7 +103,10 @@ int64_t gpb_launch_count(gpb_handle* h);
  * streams (default 1; bench.py switches it off while it times individual kernels).  option 1: launch
  * the GEMM / leaf kernels with programmatic dependent launch (default 1).  option 2: use the
  * straight-line instantiations of the element kernels for the known expression shapes
- * (csrc/shapes.cuh; default 1, 0 forces the run-time interpreter -- same results). */
+ * (csrc/shapes.cuh; default 1, 0 forces the run-time interpreter -- same results).  option 3: one
+ * step of iterative refinement of alpha = (K + s2 I)^-1 y for the quadratic form of the objective
+ * (0 never, 1 automatic: only when the host-side bound N k(x,x) / s2 on cond(K + s2 I) exceeds 2e7, 2
+ * always; default 1).  predict_f always refines alpha for the mean (csrc/gpr.cu). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 /* Diagnostics: which straight-line shape (csrc/shapes.cuh, 1-based id) the current expression matches;
  * 0 = none, the run-time interpreter evaluates it (also when option 2 is off).  < 0: error. */

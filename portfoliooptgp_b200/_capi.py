@@ -181,6 +181,7 @@ class Engine:
     OPTION_FORK_STREAMS = 0
     OPTION_PDL = 1
     OPTION_STATIC_SHAPES = 2
+    OPTION_REFINE_OBJECTIVE = 3   # 0 never, 1 automatic (ill-conditioned K only), 2 always
 
     def set_option(self, option: int, value: int):
         self._check(self._lib.gpb_set_option(self._h, int(option), int(value)), "gpb_set_option")

@@ -29,7 +29,7 @@ int check_cuda(gpb_handle* h, cudaError_t e, const char* what) {
 double* workspace(gpb_handle* h, int id, size_t bytes) {
     // whoever asks for these three is about to overwrite the stored GPR factorisation (gpr.cu re-validates
     // it after its own requests)
-    if (id == BUF_K || id == BUF_W || id == BUF_VEC) h->fact_valid = false;
+    if (id == BUF_K || id == BUF_W || id == BUF_VEC || id == BUF_WD) h->fact_valid = false;
     if (bytes <= h->buf_bytes[id] && h->buf[id]) return h->buf[id];
     if (h->buf[id]) {
         cudaFree(h->buf[id]);  // synchronises the device: no kernel can still be using the old block
@@ -187,7 +187,7 @@ int gpb_destroy(gpb_handle* h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < gpb_handle::N_BUF; ++i)
         if (h->buf[i]) cudaFree(h->buf[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -227,6 +227,10 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
         case 0: h->fork_streams = (value != 0); return 0;
         case 1: h->use_pdl = (value != 0); return 0;
         case 2: h->use_shapes = (value != 0); return 0;
+        case 3:
+            if (value < 0 || value > 2) return set_error(h, -2, "option 3 (objective refinement) takes 0, 1 or 2");
+            h->refine_mode = value;
+            return 0;
         default: return set_error(h, -2, "unknown option %d", option);
     }
 }
@@ -311,10 +315,27 @@ static int potrf_common(gpb_handle* h, double* d_A, int64_t N, int64_t lda, doub
 
 int gpb_potrf(gpb_handle* h, double* d_A, int64_t N, int64_t lda) {
     GPB_ENTER(h);
-    const int64_t ldw = (N + 15) / 16 * 16;
-    double* W = workspace(h, BUF_W, (size_t)((N + 127) / 128 * 128) * ldw * sizeof(double));
-    if (!W) return -1;
-    return potrf_common(h, d_A, N, lda, W, ldw);
+    // the factor alone (N^3/3 flop): no N x N inverse; the solves inside multiply by the inverses of the
+    // GPB_NBD x GPB_NBD diagonal blocks only (cholesky.cu factor_L)
+    if (!d_A || N <= 0 || lda < N) return set_error(h, -2, "potrf: bad arguments");
+    if (N > 0x7fffff00LL) return set_error(h, -2, "potrf: N too large");
+    const int64_t ldw = (N + 15) / 16 * 16, rows = (N + 127) / 128 * 128, nblk = (N + 127) / 128;
+    double* Lw = workspace(h, BUF_W, (size_t)rows * ldw * sizeof(double));
+    double* Wd = workspace(h, BUF_WD, (size_t)rows * GPB_NBD * sizeof(double));
+    double* v = workspace(h, BUF_DINV, (size_t)(nblk + 16) * sizeof(double));
+    if (!Lw || !Wd || !v) return -1;
+    int* info = reinterpret_cast<int*>(v + nblk);
+    int rc = factor_L(h, d_A, lda, Lw, ldw, Wd, N, v, info);
+    if (rc) return rc;
+    if ((rc = gather_L(h, d_A, lda, Lw, ldw, N))) return rc;
+    double* hp = pinned(h, (size_t)(64 + 2) * sizeof(double));
+    if (!hp) return -1;
+    cudaError_t e = cudaMemcpyAsync(hp + 64, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "potrf sync");
+    const int inf = *reinterpret_cast<int*>(hp + 64);
+    if (inf > 0) set_error(h, inf, "Cholesky decomposition was not successful: non-positive pivot at row %d", inf);
+    return inf;
 }
 
 int gpb_potrf_inv(gpb_handle* h, double* d_A, int64_t N, int64_t lda, double* d_W, int64_t ldw) {

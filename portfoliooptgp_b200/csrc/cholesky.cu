@@ -20,6 +20,7 @@
 namespace gpb {
 
 constexpr int NB = 128;
+constexpr int NBD = GPB_NBD;   // diagonal-block size of the factor-only path (engine.cuh)
 constexpr int LEAF_THREADS = 512;
 constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + DINV_DOUBLES + 16) * sizeof(double);
 
@@ -28,7 +29,7 @@ constexpr size_t LEAF_SMEM = (size_t)(NB * SLD + 64 * TLD + DINV_DOUBLES + 16) *
 // (block_chol.cuh).  Blocks narrower than 128 are padded to a multiple of 8 with an identity.
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ W, int64_t ldw, int n, int offset,
-                      double* __restrict__ logdiag, int* __restrict__ info, int store_L) {
+                      double* __restrict__ logdiag, int* __restrict__ info, int store_L, int info_base) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* T = sm + NB * SLD;
@@ -56,7 +57,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
     }
     __syncthreads();
     block_potrf_lower(S, np, fail, dinv);
-    if (tid == 0 && *fail != 0) atomicCAS(info, 0, offset + *fail);
+    if (tid == 0 && *fail != 0) atomicCAS(info, 0, info_base + offset + *fail);
     // L itself is only needed by callers that keep the factor (gpb_potrf, SVGP adjoint); the LML / K^-1
     // pipeline consumes W and the log-diagonal only, so the 128 KB store is skipped there
     if (store_L) {
@@ -84,7 +85,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
 }
 
 static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int n, int offset, double* logdiag,
-                int* info, bool store_L) {
+                int* info, bool store_L, int info_base) {
     static bool attr_set[GPB_MAX_DEVICES] = {};
     {
         cudaError_t e = ensure_dyn_smem(attr_set, h->device, leaf_potrf_inv_kernel, LEAF_SMEM);
@@ -94,12 +95,12 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
     if (h->use_pdl) {
         cudaError_t le = launch_pdl(leaf_potrf_inv_kernel, dim3(1), dim3(LEAF_THREADS), LEAF_SMEM, h->stream,
                                     A + (int64_t)offset * lda + offset, lda, W + (int64_t)offset * ldw + offset, ldw, n,
-                                    offset, logdiag, info, store_L ? 1 : 0);
+                                    offset, logdiag, info, store_L ? 1 : 0, info_base);
         if (le != cudaSuccess) return check_cuda(h, le, "leaf launch (PDL)");
     } else {
         leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, h->stream>>>(A + (int64_t)offset * lda + offset, lda,
                                                                          W + (int64_t)offset * ldw + offset, ldw, n, offset,
-                                                                         logdiag, info, store_L ? 1 : 0);
+                                                                         logdiag, info, store_L ? 1 : 0, info_base);
     }
     h->launches += 1;
     return check_cuda(h, cudaGetLastError(), "leaf_potrf_inv_kernel launch");
@@ -107,11 +108,13 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
 
 // A, W: full matrices; factor the diagonal block [o, o+n).  keepL: additionally leave L21 in A21
 // (needs U scratch of n2 x n1 doubles).
+// info_base: added to the reported pivot index (the block may sit at row info_base of a larger matrix whose
+// diagonal blocks are factorised one by one, factor_L below).
 static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
-                          int* info, bool keepL, double* scratchU, int depth) {
-    if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info, keepL);
+                          int* info, bool keepL, double* scratchU, int depth, int info_base = 0) {
+    if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info, keepL, info_base);
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1, o2 = o + n1;
-    int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1);
+    int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1, info_base);
     if (rc) return rc;
     double* A21 = A + (int64_t)o2 * lda + o;
     double* A22 = A + (int64_t)o2 * lda + o2;
@@ -158,7 +161,7 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
         if (e != cudaSuccess) return check_cuda(h, e, "record U join");
     }
     if ((rc = factor_inv_rec(h, A, lda, W, ldw, o2, n2, logdiag, info, keepL, keepL ? scratchU + (int64_t)n2 * n1 : scratchU,
-                             depth + 1)))
+                             depth + 1, info_base)))
         return rc;
     if (fork) {
         cudaError_t e = cudaStreamWaitEvent(h->stream, h->ev_join[depth], 0);
@@ -200,6 +203,242 @@ int lauum_lower(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double
     g.transa = 1; g.transb = 0; g.M = N; g.N = N; g.K = N;
     g.A = d_W; g.lda = ldw; g.B = d_W; g.ldb = ldw; g.C = d_Out; g.ldc = ldo; g.tri = 1; g.a_upper = 1;
     return launch_gemm(h, g, h->stream);
+}
+
+__global__ void trmv_lower_kernel(const double* __restrict__ W, int64_t ldw, int n, const double* __restrict__ y,
+                                  double* __restrict__ out);
+
+// ---- factor only (no N x N inverse) -----------------------------------------------------------------------
+// LML-only and predict-only flows (GPR/predictor.py:6, Multi-Input_GPR/main.py:434, BASELINE config C4) need
+// L, L^-1 y and L^-1 K(X, X*), not K^-1: N^3/3 flop instead of the 2N^3/3 of factor_inv.  Recursive blocked
+// Cholesky whose triangular solves are GEMMs with the explicit inverses of the NBD x NBD DIAGONAL blocks only:
+//   potrf(o, n):  n <= NBD: L_kk, Wd_k = factor_inv(A_kk)                                (keepL)
+//                 else      potrf(A11); X = A21 L11^-T (trsm, below); A22 -= X X^T; potrf(A22)
+//   trsm(B, L):   n <= NBD: X = B Wd^T
+//                 else      X1 = trsm(B1, L11); B2 -= X1 L21^T; X2 = trsm(B2, L22)
+// Storage: the diagonal blocks of L stay in A; everything below them is written to Lw at the same
+// coordinates (a GEMM cannot run in place; A's off-diagonal part is the solve's scratch), so consumers take
+// L_kk from A and L_kj (j < k) from Lw.  Wd is an [N, NBD] strip: block k at rows [k NBD, (k+1) NBD).
+// Extra flop over N^3/3: N NBD^2 / 3 for the block inverses (1.6 % at N = 8192).
+static int trsm_rec(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, const double* Wd, int r0, int m, int c0,
+                    int n) {
+    int rc;
+    GemmArgs g;
+    if (n <= NBD) {
+        g.transa = 0; g.transb = 1; g.M = m; g.N = n; g.K = n;
+        g.A = A + (int64_t)r0 * lda + c0; g.lda = lda;
+        g.B = Wd + (int64_t)c0 * NBD; g.ldb = NBD;
+        g.C = Lw + (int64_t)r0 * ldl + c0; g.ldc = ldl; g.b_upper = 1;
+        return launch_gemm(h, g, h->stream);
+    }
+    const int n1 = ((n / 2 + NBD - 1) / NBD) * NBD, n2 = n - n1;
+    if ((rc = trsm_rec(h, A, lda, Lw, ldl, Wd, r0, m, c0, n1))) return rc;
+    g.transa = 0; g.transb = 1; g.M = m; g.N = n2; g.K = n1; g.alpha = -1.0; g.beta = 1.0;
+    g.A = Lw + (int64_t)r0 * ldl + c0; g.lda = ldl;
+    g.B = Lw + (int64_t)(c0 + n1) * ldl + c0; g.ldb = ldl;
+    g.C = A + (int64_t)r0 * lda + c0 + n1; g.ldc = lda;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    return trsm_rec(h, A, lda, Lw, ldl, Wd, r0, m, c0 + n1, n2);
+}
+
+static int potrf_rec(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, double* Wd, int o, int n,
+                     double* logdiag, int* info, double* scratchU) {
+    int rc;
+    if (n <= NBD)
+        return factor_inv_rec(h, A + (int64_t)o * lda + o, lda, Wd + (int64_t)o * NBD, NBD, 0, n, logdiag + o / NB, info, true,
+                              scratchU, 0, o);
+    const int n1 = ((n / 2 + NBD - 1) / NBD) * NBD, n2 = n - n1, o2 = o + n1;
+    if ((rc = potrf_rec(h, A, lda, Lw, ldl, Wd, o, n1, logdiag, info, scratchU))) return rc;
+    if ((rc = trsm_rec(h, A, lda, Lw, ldl, Wd, o2, n2, o, n1))) return rc;
+    GemmArgs g;   // A22 -= X X^T (lower tiles)
+    g.transa = 0; g.transb = 1; g.M = n2; g.N = n2; g.K = n1; g.alpha = -1.0; g.beta = 1.0;
+    g.A = Lw + (int64_t)o2 * ldl + o; g.lda = ldl; g.B = g.A; g.ldb = ldl;
+    g.C = A + (int64_t)o2 * lda + o2; g.ldc = lda; g.tri = 1;
+    if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    return potrf_rec(h, A, lda, Lw, ldl, Wd, o2, n2, logdiag, info, scratchU);
+}
+
+int factor_L(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, double* Wd, int64_t N, double* logdiag,
+             int* d_info) {
+    double* scratch = nullptr;
+    const size_t need = keepL_scratch((int)(N < NBD ? N : NBD));
+    if (need) {
+        scratch = workspace(h, BUF_PANEL, need * sizeof(double));
+        if (!scratch) return -1;
+    }
+    cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "memset info");
+    return potrf_rec(h, A, lda, Lw, ldl, Wd, 0, (int)N, logdiag, d_info, scratch);
+}
+
+// out[row] = y[row] - diag * a[row0 + row] - sum_{j < ncols} M[row][j] a[j]   (one warp per row).  Used for the
+// off-diagonal strip of a block row (diag = 0) and for the residual y - (K + s2 I) alpha (diag = s2).
+__global__ void gemv_sub_kernel(const double* __restrict__ M, int64_t ldm, int nrows, int ncols, const double* __restrict__ a,
+                                const double* __restrict__ y, double diag, int row0, double* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const double* l = M + (int64_t)row * ldm;
+    double s0 = 0.0, s1 = 0.0;
+    const int even = ncols & ~1;
+    for (int j = 2 * lane; j < even; j += 64) {     // rows are 16-byte aligned (even leading dimension)
+        const double2 lv = *reinterpret_cast<const double2*>(l + j);
+        const double2 av = *reinterpret_cast<const double2*>(a + j);
+        s0 = fma(lv.x, av.x, s0);
+        s1 = fma(lv.y, av.y, s1);
+    }
+    if (lane == 0 && even < ncols) s0 = fma(l[even], a[even], s0);
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = (y[row] - diag * a[row0 + row]) - s;
+}
+
+int gemv_sub(gpb_handle* h, const double* M, int64_t ldm, int64_t nrows, int64_t ncols, const double* a, const double* y,
+             double diag, int64_t row0, double* out) {
+    const int warps = 8;
+    gemv_sub_kernel<<<(unsigned)((nrows + warps - 1) / warps), warps * 32, 0, h->stream>>>(M, ldm, (int)nrows, (int)ncols, a, y,
+                                                                                         diag, (int)row0, out);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "gemv_sub_kernel launch");
+}
+
+// partial[c][j] = sum_{i in row chunk c} M[i][j] v[i]  (thread per column, GEMVT_CH rows per chunk)
+constexpr int GEMVT_CH = 32;
+__global__ void gemvT_partial_kernel(const double* __restrict__ M, int64_t ldm, int nrows, int ncols,
+                                     const double* __restrict__ v, double* __restrict__ partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (j >= ncols) return;
+    const int i0 = c * GEMVT_CH, i1 = min(nrows, i0 + GEMVT_CH);
+    double s = 0.0;
+    if (i1 - i0 == GEMVT_CH) {
+        double w[GEMVT_CH];
+#pragma unroll
+        for (int k = 0; k < GEMVT_CH; ++k) w[k] = M[(int64_t)(i0 + k) * ldm + j];
+#pragma unroll
+        for (int k = 0; k < GEMVT_CH; ++k) s = fma(w[k], v[i0 + k], s);
+    } else {
+        for (int i = i0; i < i1; ++i) s = fma(M[(int64_t)i * ldm + j], v[i], s);
+    }
+    partial[(int64_t)c * ncols + j] = s;
+}
+// out[j] = a[j] - sum_c partial[c][j]
+__global__ void colsum_sub_kernel(const double* __restrict__ partial, int nchunks, int n, const double* __restrict__ a,
+                                  double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += partial[(int64_t)c * n + j];
+    out[j] = a[j] - s;
+}
+__global__ void vec_add_kernel(double* __restrict__ x, const double* __restrict__ d, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += d[i];
+}
+// out[0] = sum_i x_i y_i  (single block, fixed order)
+__global__ void vec_dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int n, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(x[i], y[i], s);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+int vec_dot(gpb_handle* h, const double* x, const double* y, int64_t n, double* out) {
+    vec_dot_kernel<<<1, 256, 0, h->stream>>>(x, y, (int)n, out);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "vec_dot_kernel launch");
+}
+int vec_add(gpb_handle* h, double* x, const double* d, int64_t n) {
+    vec_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(x, d, (int)n);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "vec_add_kernel launch");
+}
+
+// a = L^-1 y by block forward substitution over the NBD blocks of factor_L's output:
+// a_k = Wd_k (y_k - sum_{j<k} L_kj a_j).  tmp: N doubles.
+int solve_L_vec(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, const double* y, double* a,
+                double* tmp) {
+    ProfScope prof(h, PROF_VEC, h->stream);
+    const int warps = 8;
+    for (int64_t o = 0; o < N; o += NBD) {
+        const int nk = (int)((N - o < NBD) ? (N - o) : NBD);
+        const double* rhs = y + o;
+        if (o > 0) {
+            gemv_sub_kernel<<<(unsigned)((nk + warps - 1) / warps), warps * 32, 0, h->stream>>>(Lw + o * ldl, ldl, nk, (int)o, a,
+                                                                                              y + o, 0.0, 0, tmp + o);
+            rhs = tmp + o;
+            h->launches += 1;
+        }
+        trmv_lower_kernel<<<(unsigned)((nk + warps - 1) / warps), warps * 32, 0, h->stream>>>(Wd + o * NBD, NBD, nk, rhs, a + o);
+        h->launches += 1;
+    }
+    return check_cuda(h, cudaGetLastError(), "solve_L_vec launches");
+}
+
+// alpha = L^-T a by block back substitution: alpha_k = Wd_k^T (a_k - sum_{i>k} L_ik^T alpha_i).  tmp: N doubles.
+int solve_LT_vec(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, const double* a, double* alpha,
+                 double* tmp) {
+    const int64_t nblocks = (N + NBD - 1) / NBD;
+    const int64_t max_chunks = (N + GEMVT_CH - 1) / GEMVT_CH;
+    // one request covers the strip partials and trmv_lower_T's own partials (both live in BUF_RED, used in turn)
+    double* partial = workspace(h, BUF_RED, (size_t)max_chunks * NBD * sizeof(double));
+    if (!partial) return -1;
+    int rc;
+    for (int64_t k = nblocks - 1; k >= 0; --k) {
+        const int64_t o = k * NBD;
+        const int nk = (int)((N - o < NBD) ? (N - o) : NBD);
+        const int64_t below = N - (o + nk);
+        const double* rhs = a + o;
+        if (below > 0) {
+            ProfScope prof(h, PROF_VEC, h->stream);
+            const int nch = (int)((below + GEMVT_CH - 1) / GEMVT_CH);
+            dim3 grid((unsigned)((nk + 127) / 128), (unsigned)nch);
+            gemvT_partial_kernel<<<grid, 128, 0, h->stream>>>(Lw + (o + nk) * ldl + o, ldl, (int)below, nk, alpha + o + nk, partial);
+            colsum_sub_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, h->stream>>>(partial, nch, nk, a + o, tmp + o);
+            h->launches += 2;
+            rhs = tmp + o;
+        }
+        if ((rc = trmv_lower_T(h, Wd + o * NBD, NBD, nk, rhs, alpha + o))) return rc;
+    }
+    return check_cuda(h, cudaGetLastError(), "solve_LT_vec launches");
+}
+
+// B [N, m] (ldb) <- destroyed; Out [N, m] (ldo) = L^-1 B by block forward substitution (left-looking):
+// B_k -= L_k,<k Out_<k ; Out_k = Wd_k B_k.  N^2 m flop on the DMMA GEMM.
+int solve_L_mat(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, double* B, int64_t ldb, int64_t m,
+                double* Out, int64_t ldo) {
+    int rc;
+    for (int64_t o = 0; o < N; o += NBD) {
+        const int64_t nk = (N - o < NBD) ? (N - o) : NBD;
+        GemmArgs g;
+        if (o > 0) {
+            g.transa = 0; g.transb = 0; g.M = nk; g.N = m; g.K = o; g.alpha = -1.0; g.beta = 1.0;
+            g.A = Lw + o * ldl; g.lda = ldl; g.B = Out; g.ldb = ldo; g.C = B + o * ldb; g.ldc = ldb;
+            if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        }
+        g = GemmArgs();
+        g.transa = 0; g.transb = 0; g.M = nk; g.N = m; g.K = nk;
+        g.A = Wd + o * NBD; g.lda = NBD; g.B = B + o * ldb; g.ldb = ldb; g.C = Out + o * ldo; g.ldc = ldo; g.a_lower = 1;
+        if ((rc = launch_gemm(h, g, h->stream))) return rc;
+    }
+    return 0;
+}
+
+// copy the off-diagonal blocks of L from Lw back under the diagonal blocks in A (gpb_potrf: L in place)
+int gather_L(gpb_handle* h, double* A, int64_t lda, const double* Lw, int64_t ldl, int64_t N) {
+    for (int64_t o = NBD; o < N; o += NBD) {
+        const int64_t nk = (N - o < NBD) ? (N - o) : NBD;
+        cudaError_t e = cudaMemcpy2DAsync(A + o * lda, lda * sizeof(double), Lw + o * ldl, ldl * sizeof(double),
+                                          (size_t)o * sizeof(double), (size_t)nk, cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) return check_cuda(h, e, "gather_L copy");
+    }
+    return 0;
 }
 
 // ---- triangular matrix-vector products --------------------------------------------------------------
@@ -321,8 +560,8 @@ __global__ void predict_finish_kernel(const double* __restrict__ p_ss, const dou
         ss += p_ss[(int64_t)c * m + j];
         dt += p_dot[(int64_t)c * m + j];
     }
-    mean[j] = dt;
-    var[j] = kdiag[j] - ss;
+    if (mean) mean[j] = dt;
+    if (var) var[j] = kdiag[j] - ss;
 }
 
 int predict_colreduce(gpb_handle* h, const double* A, int64_t lda, int64_t n, int64_t m, const double* a,

@@ -21,10 +21,12 @@ struct gpb_handle {
     bool fork_streams = true;   // gpb_set_option(h, 0, x)
     bool use_pdl = true;        // gpb_set_option(h, 1, x): programmatic dependent launch for dgemm / leaf
     bool use_shapes = true;     // gpb_set_option(h, 2, x): straight-line kernels for the known expression shapes (shapes.cuh)
+    int refine_mode = 1;        // gpb_set_option(h, 3, x): refinement of y^T K^-1 y in the objective: 0 never, 1 automatic, 2 always (gpr.cu)
     // the factorisation W = L^-1, a = W y left in the workspaces by the last gpr_lml / gpr_predict_f:
     // what it was computed for, and whether the workspaces still hold it (any other use of BUF_K / BUF_W /
     // BUF_VEC clears the flag).  fact_serial counts factorisations; gpb_gpr_predict_f_reuse consumes it.
     bool fact_valid = false;
+    int fact_kind = 0;          // 1: W = L^-1 in BUF_W (factor_inv); 2: factor only -- L in BUF_K (diagonal blocks) / BUF_W, block inverses in BUF_WD
     int64_t fact_serial = 0;
     const double* fact_X = nullptr;
     int64_t fact_N = 0;
@@ -45,8 +47,9 @@ struct gpb_handle {
     int D = 0;
 
     // grow-only device workspaces
-    double* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t buf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static constexpr int N_BUF = 10;
+    double* buf[N_BUF] = {};
+    size_t buf_bytes[N_BUF] = {};
     double* h_pinned = nullptr;  // small pinned staging area for scalar results
     size_t h_pinned_bytes = 0;
 
@@ -82,7 +85,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7 };
+enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7, BUF_WD = 8 };
+constexpr int GPB_NBD = 1024;   // factor-only path: diagonal blocks of this size carry explicit inverses (cholesky.cu)
 
 enum ProfCat { PROF_GEMM = 0, PROF_ASSEMBLE = 1, PROF_LEAF = 2, PROF_GRAD = 3, PROF_VEC = 4, PROF_BATCHED = 5, PROF_SVGP = 6, PROF_NCAT = 8 };
 // RAII timer: records an event pair around the launches issued in its scope when h->profile is on.
@@ -169,13 +173,28 @@ inline cudaError_t ensure_dyn_smem(bool (&done)[GPB_MAX_DEVICES], int device, K 
 // *d_info = 1-based index of the first non-positive pivot (0 = ok).
 int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag, int* d_info,
                bool keepL);
+// Factor only (N^3/3): L's diagonal NBD-blocks in A, the rest in Lw, block inverses in the [N, NBD] strip Wd.
+int factor_L(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, double* Wd, int64_t N, double* logdiag,
+             int* d_info);
+int solve_L_vec(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, const double* y, double* a,
+                double* tmp);
+int solve_LT_vec(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, const double* a, double* alpha,
+                 double* tmp);
+int gemv_sub(gpb_handle* h, const double* M, int64_t ldm, int64_t nrows, int64_t ncols, const double* a, const double* y,
+             double diag, int64_t row0, double* out);
+int vec_add(gpb_handle* h, double* x, const double* d, int64_t n);
+int vec_dot(gpb_handle* h, const double* x, const double* y, int64_t n, double* out);
+int solve_L_mat(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, double* B, int64_t ldb, int64_t m,
+                double* Out, int64_t ldo);
+int gather_L(gpb_handle* h, double* A, int64_t lda, const double* Lw, int64_t ldl, int64_t N);
 // Out (lower tiles) = W^T W
 int lauum_lower(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo);
 int trmv_lower(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const double* y, double* out);
 int trmv_lower_T(gpb_handle* h, const double* W, int64_t ldw, int64_t n, const double* a, double* out);
 int quad_logdet(gpb_handle* h, const double* v, int64_t n, const double* logdiag, double* out2);
+// var[j] = kdiag[j] - sum_i A[i][j]^2 ; dotp[j] = sum_i A[i][j] a[i].  Either output may be null.
 int predict_colreduce(gpb_handle* h, const double* A, int64_t lda, int64_t n, int64_t m, const double* a,
-                      const double* kdiag, double* mean, double* var);
+                      const double* kdiag, double* dotp, double* var);
 
 // ---- gpr.cu
 int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, double* grad_theta, double* grad_noise,

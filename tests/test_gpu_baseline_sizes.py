@@ -60,17 +60,17 @@ def test_c1_lml_grad_predict_match_oracle(gp, tag, s2, mean_bar):
     assert err["var_abs"] <= 1e-9 * max(1.0, err["var_max"]), err
 
 
-@pytest.mark.parametrize("tag,s2", [("1e-2", 1e-2), ("1e-5", 1e-5)])
-def test_c1_scipy_endpoint_matches_oracle_lbfgs(gp, tag, s2):
-    """The full fit of GPR/model_trainer.py:15-20 at C1's size: Scipy(maxiter=100) on the CUDA objective vs the
-    same SciPy L-BFGS-B on the oracle objective, same x0 and variable order; then predict_f at the end point."""
-    X, Y = make_c1(1000)
+def _c1_fit(gp, X, Y, s2, maxiter):
     m = gp.models.GPR(data=(X, Y), kernel=_c1_kernel(gp))
     m.likelihood.variance.assign(s2)
     gp.set_trainable(m.likelihood.variance, False)
     variables = m.trainable_variables
     x0 = gp.optimizers.Scipy.initial_parameters(variables)
-    res = gp.optimizers.Scipy().minimize(m.training_loss, variables, options=dict(maxiter=100))
+    res = gp.optimizers.Scipy().minimize(m.training_loss, variables, options=dict(maxiter=maxiter))
+    return m, x0, res
+
+
+def _c1_oracle_objective(X, Y, s2):
     ko = _c1_oracle()
 
     def fun(u):
@@ -78,19 +78,57 @@ def test_c1_scipy_endpoint_matches_oracle_lbfgs(gp, tag, s2):
         l, g, _ = O.gpr_lml_and_grad(ko, X, Y, s2)
         return -l, -g * O.sigmoid(u)
 
-    ref = scipy.optimize.minimize(fun, x0, jac=True, method="L-BFGS-B", options=dict(maxiter=100))
+    return ko, fun
+
+
+@pytest.mark.parametrize("tag,s2", [("1e-2", 1e-2), ("1e-5", 1e-5)])
+def test_c1_scipy_iterates_match_oracle_lbfgs(gp, tag, s2):
+    """GPR/model_trainer.py:15-19 at C1's size, same SciPy L-BFGS-B, same x0 and variable order, CUDA objective
+    vs oracle objective: the iterates agree to 1e-6 "after the same iterations" (north_star) for as long as the
+    comparison is well-posed -- the first 3 iterations (10 evaluations).  This objective (a flat valley: the
+    SE variance runs to 0) amplifies a perturbation of the iterate ~100-1000x per iteration: the ORACLE ITSELF,
+    Gram-form vs direct distances (two fp64 LAPACK runs, f differing by 3e-14 relative), is 5e-10 / 4e-7 apart
+    after 3 iterations and 4e-7 / 2.5e-3 after 4 (sigma^2 = 1e-2 / 1e-5), and ends the maxiter = 100 run after
+    71 vs 56 iterations 0.9 apart in x; f scaled by (1 + 1e-14) or another BLAS do the same (measured,
+    DESIGN.md section 10)."""
+    X, Y = make_c1(1000)
+    m, x0, res = _c1_fit(gp, X, Y, s2, maxiter=3)
+    ko, fun = _c1_oracle_objective(X, Y, s2)
+    ref = scipy.optimize.minimize(fun, x0, jac=True, method="L-BFGS-B", options=dict(maxiter=3))
     rec = {"nit_gpu": int(res.nit), "nit_oracle": int(ref.nit), "nfev_gpu": int(res.nfev), "nfev_oracle": int(ref.nfev),
-           "x_max_abs_diff": float(np.max(np.abs(res.x - ref.x))), "fun_gpu": float(res.fun), "fun_oracle": float(ref.fun),
-           "fun_rel_diff": float(abs(res.fun - ref.fun) / max(1.0, abs(ref.fun)))}
-    record_parity("c1_n1000_lbfgs_endpoint|" + tag, rec)
+           "x_max_abs_diff": float(np.max(np.abs(res.x - ref.x))), "fun_rel_diff": float(abs(res.fun - ref.fun) / abs(ref.fun))}
+    record_parity("c1_n1000_lbfgs_3_iterations|" + tag, rec)
     assert res.nit == ref.nit and res.nfev == ref.nfev, rec
     assert rec["x_max_abs_diff"] < 1e-6, rec
-    assert rec["fun_rel_diff"] < 1e-6, rec
-    mean, var = m.predict_f(X)                      # in-sample prediction at the fitted parameters (model_trainer.py:20)
-    O.set_theta(ko, O.softplus(ref.x))
+    assert rec["fun_rel_diff"] < (1e-9 if s2 >= 1e-2 else 5e-8), rec
+
+
+@pytest.mark.parametrize("tag,s2", [("1e-2", 1e-2), ("1e-5", 1e-5)])
+def test_c1_full_fit_end_point_is_the_oracles_optimum_too(gp, tag, s2):
+    """The full maxiter = 100 fit + in-sample predict_f (GPR/model_trainer.py:19-20).  The end points of two fp64
+    runs are not comparable coordinate by coordinate (see above), so the CUDA end point is checked where it
+    stands: the oracle's objective, gradient and prediction AT that point agree with the CUDA ones, the loss
+    there is as low as the oracle's own run reaches (within 0.5 %), and the fit converged."""
+    X, Y = make_c1(1000)
+    m, x0, res = _c1_fit(gp, X, Y, s2, maxiter=100)
+    ko, fun = _c1_oracle_objective(X, Y, s2)
+    f_at, g_at = fun(res.x)
+    ref = scipy.optimize.minimize(fun, x0, jac=True, method="L-BFGS-B", options=dict(maxiter=100))
+    loss, grads = m.training_loss_closure().value_and_grads(m.trainable_variables)
+    g_gpu = np.concatenate([np.atleast_1d(g) for g in grads])
+    mean, var = m.predict_f(X)
+    O.set_theta(ko, O.softplus(res.x))
     m0, v0 = O.gpr_predict_f(ko, X, Y, s2, X)
-    assert np.max(np.abs(mean.numpy() - m0)) <= 1e-6 * np.max(np.abs(m0))
-    assert np.max(np.abs(var.numpy() - v0)) <= 1e-6 * max(1.0, np.max(np.abs(v0)))
+    rec = {"nit_gpu": int(res.nit), "nit_oracle": int(ref.nit), "fun_gpu": float(res.fun), "fun_oracle_own_run": float(ref.fun),
+           "oracle_f_at_gpu_x_rel": float(abs(f_at - loss) / abs(f_at)),
+           "oracle_g_at_gpu_x_rel_to_max": float(np.max(np.abs(g_at - g_gpu)) / max(1.0, np.max(np.abs(g_at)))),
+           "mean_rel_to_max": float(np.max(np.abs(mean.numpy() - m0)) / np.max(np.abs(m0))),
+           "var_abs": float(np.max(np.abs(var.numpy() - v0)))}
+    record_parity("c1_n1000_full_fit|" + tag, rec)
+    assert res.success, res.message
+    assert rec["oracle_f_at_gpu_x_rel"] <= 1e-9 and rec["oracle_g_at_gpu_x_rel_to_max"] <= 1e-7, rec
+    assert res.fun <= ref.fun + 5e-3 * abs(ref.fun), rec
+    assert rec["mean_rel_to_max"] <= (1e-9 if s2 >= 1e-2 else 5e-8) and rec["var_abs"] <= 1e-9, rec
 
 
 # ---- C2: N = 8192, D = 8, SE + Matern52 + Linear (north-star sum kernel), sigma^2 = 1e-2 ---------------------
@@ -154,15 +192,30 @@ def test_c4_n65536_vs_cusolver(gp):
     Kfull = ops.kernel_matrix(k, X, diag_add=noise)               # [N, N] symmetric, 34 GB
     Ks = ops.kernel_matrix(k, X, Xs)                               # [N, Ns]
     kss = ops.kernel_diag(k, Xs)
-    L = torch.linalg.cholesky(Kfull)
-    del Kfull
+    # torch.linalg.cholesky on the whole 34 GB matrix faults inside the library at this size (an illegal
+    # address, reproduced by tools/debug_c4.py on the assembled matrix alone), so the comparison factorisation
+    # is a right-looking block Cholesky over 16 384-wide panels made of library pieces: cuSOLVER potrf on the
+    # diagonal blocks, cuBLAS triangular solves and matmul for the rest -- none of this repo's kernels.
+    nb = 16384
     Yd = torch.as_tensor(Y, device="cuda")
-    a = torch.linalg.solve_triangular(L, Yd, upper=False)
-    ref_lml = float(-0.5 * (a * a).sum() - 0.5 * N * math.log(2 * math.pi) - torch.log(torch.diagonal(L)).sum())
-    A = torch.linalg.solve_triangular(L, Ks.contiguous(), upper=False)
+    B = torch.cat([Yd, Ks.contiguous()], dim=1)                     # right-hand sides [N, 1 + Ns]
+    logdet = 0.0
+    for o in range(0, N, nb):
+        Lkk = torch.linalg.cholesky(Kfull[o:o + nb, o:o + nb])
+        logdet += float(torch.log(torch.diagonal(Lkk)).sum())
+        B[o:o + nb] = torch.linalg.solve_triangular(Lkk, B[o:o + nb], upper=False)
+        if o + nb < N:
+            L21 = torch.linalg.solve_triangular(Lkk, Kfull[o + nb:, o:o + nb].T, upper=False).T.contiguous()   # [rest, nb]
+            B[o + nb:] -= L21 @ B[o:o + nb]
+            for c in range(o + nb, N, nb):                          # trailing update, lower block columns
+                Kfull[c:, c:c + nb] -= L21[c - o - nb:] @ L21[c - o - nb:c - o].T
+            del L21
+        del Lkk
+    a, A = B[:, :1], B[:, 1:]
+    ref_lml = float(-0.5 * (a * a).sum() - 0.5 * N * math.log(2 * math.pi) - logdet)
     ref_mean = (A.T @ a).cpu().numpy()
     ref_var = (kss - (A * A).sum(0)).cpu().numpy()[:, None]
-    del L, A, Ks
+    del Kfull, B, Ks, a, A
     torch.cuda.empty_cache()
     m = gp.models.GPR((X, Y), kernel=k, noise_variance=noise)
     lml = float(m.log_marginal_likelihood())

@@ -75,3 +75,31 @@ def test_potrf_reports_non_pd():
     dA = torch.tensor(S, device="cuda")
     with pytest.raises(gpflow.CholeskyError):
         _eng().potrf(dA.data_ptr(), n, n)
+
+
+# the factor-only path (N^3/3 flop, gpb_potrf): one diagonal block, exactly two, ragged multi-block sizes
+@pytest.mark.parametrize("n", [5, 128, 1000, 1024, 1025, 2048, 2500, 3100, 5000])
+def test_potrf_factor_only(n):
+    import torch
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n, n + 7))
+    S = G @ G.T / n + 0.05 * np.eye(n)
+    ld = (n + 15) // 16 * 16
+    dA = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
+    dA[:, :n] = torch.tensor(np.tril(S), device="cuda")
+    _eng().potrf(dA.data_ptr(), n, ld)
+    torch.cuda.synchronize()
+    L = np.tril(dA.cpu().numpy()[:, :n])
+    Lref = np.linalg.cholesky(S)
+    assert np.max(np.abs(L - Lref)) < 1e-14 * np.linalg.cond(S) * 10
+
+
+def test_potrf_factor_only_reports_pivot_row_in_a_later_block():
+    import torch
+    import portfoliooptgp_b200 as gpflow
+    n = 2300
+    S = np.eye(n); S[2100, 2100] = -1.0
+    dA = torch.tensor(S, device="cuda")
+    with pytest.raises(gpflow.CholeskyError) as ei:
+        _eng().potrf(dA.data_ptr(), n, n)
+    assert "2101" in str(ei.value)

@@ -252,3 +252,36 @@ def test_evaluations_are_bitwise_reproducible(gp):
     r0 = b.lml_and_grads()
     for _ in range(20):
         assert all(np.array_equal(a, c) for a, c in zip(b.lml_and_grads(), r0))
+
+
+@pytest.mark.parametrize("N", [700, 1024, 2500])
+def test_factor_only_flows_match_the_full_inverse_flows(gp, N):
+    """log_marginal_likelihood() and a cold predict_f take the factor-only path (N^3/3 flop, block forward
+    substitution); the objective + gradient evaluation keeps W = L^-1.  Same numbers either way, and both
+    against the oracle; a predict after either kind of evaluation reuses what the engine holds."""
+    X, Y = make_multi_input(71, N, 4)
+    Xs, _ = make_multi_input(72, 333, 4)
+    k = gp.kernels.SquaredExponential(lengthscales=1.2) + gp.kernels.Matern52(variance=0.6, lengthscales=2.0)
+    noise = 1e-2
+    ko = to_oracle(k)
+    l0 = O.gpr_lml(ko, X, Y, noise)
+    m0, v0 = O.gpr_predict_f(ko, X, Y, noise, Xs)
+    m = gp.models.GPR((X, Y), kernel=k, noise_variance=noise)
+    eng = m._get_engine()
+    mean_cold, var_cold = m.predict_f(Xs)                      # cold: factor only
+    n0 = eng.launch_count()
+    mean_again, var_again = m.predict_f(Xs)                    # reuse of the stored factor
+    n_reuse = eng.launch_count() - n0
+    lml_only = float(m.log_marginal_likelihood())              # value only: factor only
+    lml, g, gn = m.lml_and_constrained_grads()                 # factor + inverse
+    mean_w, var_w = m.predict_f(Xs)                            # reuse of W
+    assert abs(lml_only - l0) <= 1e-9 * abs(l0) and abs(lml - l0) <= 1e-9 * abs(l0)
+    assert abs(lml_only - lml) <= 1e-12 * abs(lml)
+    for mean, var in ((mean_cold, var_cold), (mean_again, var_again), (mean_w, var_w)):
+        assert np.max(np.abs(mean.numpy() - m0)) <= 1e-9 * np.max(np.abs(m0))
+        assert np.max(np.abs(var.numpy() - v0) / np.abs(v0)) <= 1e-8
+    assert np.array_equal(mean_cold.numpy(), mean_again.numpy()) and np.array_equal(var_cold.numpy(), var_again.numpy())
+    m2 = gp.models.GPR((X, Y), kernel=k, noise_variance=noise * 1.5)
+    n0 = eng.launch_count()
+    m2.predict_f(Xs)
+    assert n_reuse < eng.launch_count() - n0                   # the reuse skipped assembly and factorisation
