@@ -106,7 +106,12 @@ int64_t gpb_launch_count(gpb_handle* h);
  * (csrc/shapes.cuh; default 1, 0 forces the run-time interpreter -- same results).  option 3: one
  * step of iterative refinement of alpha = (K + s2 I)^-1 y for the quadratic form of the objective
  * (0 never, 1 automatic: only when the host-side bound N k(x,x) / s2 on cond(K + s2 I) exceeds 2e7, 2
- * always; default 1).  predict_f always refines alpha for the mean (csrc/gpr.cu). */
+ * always; default 1).  predict_f always refines alpha for the mean (csrc/gpr.cu).  option 4: the
+ * pipelined right-looking factorisation over two SM partitions (green contexts; csrc/partition.cu,
+ * csrc/cholesky.cu) for N >= 3072 (default 0 = the single-partition recursion: on B200 the pipeline's
+ * rank-1024 products run at 0.90 of the recursion's large-K products and the 8 reserved SMs cost 5 %,
+ * which outweighs the hidden latency -- 22.8 vs 21.3 ms at N = 8192, profiles/r02_pipeline_ab.txt;
+ * silently off when the driver cannot create the partitions). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 /* Diagnostics: which straight-line shape (csrc/shapes.cuh, 1-based id) the current expression matches;
  * 0 = none, the run-time interpreter evaluates it (also when option 2 is off).  < 0: error. */

@@ -182,6 +182,7 @@ class Engine:
     OPTION_PDL = 1
     OPTION_STATIC_SHAPES = 2
     OPTION_REFINE_OBJECTIVE = 3   # 0 never, 1 automatic (ill-conditioned K only), 2 always
+    OPTION_PIPELINE = 4           # two-partition pipelined factorisation for N >= 3072 (default off: measured slower)
 
     def set_option(self, option: int, value: int):
         self._check(self._lib.gpb_set_option(self._h, int(option), int(value)), "gpb_set_option")

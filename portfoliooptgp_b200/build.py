@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgpb200.so")
-SOURCES = ["capi.cu", "assemble.cu", "dgemm.cu", "cholesky.cu", "gpr.cu", "batched.cu", "batched_generic.cu", "batched_shapes.cu", "svgp.cu", "prep.cu"]
+SOURCES = ["capi.cu", "assemble.cu", "dgemm.cu", "cholesky.cu", "gpr.cu", "batched.cu", "batched_generic.cu", "batched_shapes.cu", "svgp.cu", "prep.cu", "partition.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

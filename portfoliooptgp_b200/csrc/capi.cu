@@ -179,6 +179,7 @@ int gpb_create(gpb_handle** out, int device) {
         cudaEventCreateWithFlags(&h->ev_fork[d], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_join[d], cudaEventDisableTiming);
     }
+    partitions_create(h);
     *out = h;
     return 0;
 }
@@ -187,6 +188,7 @@ int gpb_destroy(gpb_handle* h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
+    partitions_destroy(h);
     for (int i = 0; i < gpb_handle::N_BUF; ++i)
         if (h->buf[i]) cudaFree(h->buf[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -227,6 +229,7 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
         case 0: h->fork_streams = (value != 0); return 0;
         case 1: h->use_pdl = (value != 0); return 0;
         case 2: h->use_shapes = (value != 0); return 0;
+        case 4: h->use_pipeline = (value != 0); return 0;
         case 3:
             if (value < 0 || value > 2) return set_error(h, -2, "option 3 (objective refinement) takes 0, 1 or 2");
             h->refine_mode = value;

@@ -14,6 +14,8 @@
 // Every O(N^3) flop runs in dgemm.cu on the FP64 tensor pipe; the only non-GEMM work is the
 // 128x128 leaf (block_chol.cuh), one CTA, latency-bound.
 // Flops: factor N^3/3 + inverse N^3/3 + lauum N^3/3 = N^3.
+#include <stdlib.h>
+
 #include "block_chol.cuh"
 #include "engine.cuh"
 
@@ -196,6 +198,162 @@ int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, in
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) return check_cuda(h, e, "memset info");
     return factor_inv_rec(h, A, lda, W, ldw, 0, (int)N, logdiag, d_info, keepL, scratch, 0);
+}
+
+// ---- pipelined factor + inverse (+ K^-1) over two SM partitions -------------------------------------------
+// The recursion above is latency-bound at its bottom: at N = 8192 the 64 one-CTA leaves and ~240 small
+// products are 5.3 of 21.4 ms, most of it exposed, because every product above them needs the finished
+// inverse of its whole left neighbour.  A right-looking blocked formulation removes that dependency: with
+// block size b (1024) and blocks k = 0 .. nb-1,
+//   D_k   L_kk, W_kk = factor_inv(A_kk)                                   the latency-bound chain
+//   P_k   T[k+1:, k] = A[k+1:, k] W_kk^T                (= L[k+1:, k], kept in W's storage)
+//   Sa_k  A[k+1:, k+1] -= T[k+1:, k] T[k+1, k]^T        next block column only: D_k+1 may start
+//   Sb_k  A[k+2:, k+2:] -= T[k+2:, k] T[k+2:, k]^T      rest of the trailing update
+//   R_k   V = T[k, :k] W[:k, :k]  (into A[k, :k]);  W[k, :k] = -W_kk V      row k of the inverse
+//   Q_k   K^-1[k, :k+1] = W_kk^T W[k, :k+1];  K^-1[:k, :k] += W[k, :k]^T W[k, :k]   (into A, rows <= k are dead)
+// D_k+1 depends on Sa_k only, so it runs in the small SM partition (partition.cu) BESIDE Sb_k, R_k, Q_k in the
+// bulk partition: two in-order streams, D on one, everything else on the other, two events per step.  Same
+// flop count as the recursion (N^3 with K^-1), all of it in products with K = b and large M, N.  D_0 (nothing
+// to hide behind) and the last step's R, Q (no D left to run beside them) use the whole device.
+// Storage is the recursion's: A ends as the lower tiles of K^-1 (want_kinv) and W as L^-1.
+struct StreamSwap {
+    gpb_handle* h;
+    cudaStream_t s0;
+    cudaStream_t side0[gpb_handle::MAX_DEPTH];
+    StreamSwap(gpb_handle* h_, cudaStream_t s, const cudaStream_t* sides) : h(h_), s0(h_->stream) {
+        h->stream = s;
+        for (int i = 0; i < gpb_handle::MAX_DEPTH; ++i) {
+            side0[i] = h->side[i];
+            h->side[i] = sides[i];
+        }
+    }
+    ~StreamSwap() {
+        h->stream = s0;
+        for (int i = 0; i < gpb_handle::MAX_DEPTH; ++i) h->side[i] = side0[i];
+    }
+};
+
+static int pipe_block() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPB_PIPE_B");
+        v = e ? atoi(e) : 1024;
+        if (v < NB || v % NB != 0) v = 1024;
+    }
+    return v;
+}
+
+bool pipeline_applies(const gpb_handle* h, int64_t N) {
+    // (with the stream forks switched off -- bench.py's per-kernel timing -- the same task list runs on the
+    // caller's stream alone)
+    return h->use_pipeline && (h->part_ok || !h->fork_streams) && N >= 3 * (int64_t)pipe_block();
+}
+
+int factor_inv_pipelined(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag,
+                         int* d_info, bool want_kinv, cudaEvent_t* ev_W_ready) {
+    const int b = pipe_block();
+    const int nb = (int)((N + b - 1) / b);
+    const bool serial = !h->fork_streams || !h->part_ok;
+    cudaStream_t S0 = h->stream, M = serial ? h->stream : h->part_bulk, C = serial ? h->stream : h->part_crit;
+    auto off = [&](int k) { return (int64_t)k * b; };
+    auto size = [&](int k) { return (int)((N - off(k) < b) ? (N - off(k)) : b); };
+    auto evD = [&](int k) { return partition_event(h, 2 * (size_t)k); };
+    auto evSa = [&](int k) { return partition_event(h, 2 * (size_t)k + 1); };
+    cudaEvent_t ev_start = partition_event(h, 2 * (size_t)nb), ev_bulk = partition_event(h, 2 * (size_t)nb + 1),
+                ev_W = partition_event(h, 2 * (size_t)nb + 2), ev_crit = partition_event(h, 2 * (size_t)nb + 3);
+    if (!ev_start || !ev_bulk || !ev_W || !ev_crit || !evD(nb - 1) || !evSa(nb - 1)) return set_error(h, -1, "pipeline: event creation failed");
+    int rc;
+    cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), S0);
+    if (e != cudaSuccess) return check_cuda(h, e, "memset info");
+#define GPB_CU(call, what)                                  \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return check_cuda(h, e_, what); \
+    } while (0)
+    // D_0 on the caller's stream (whole device)
+    if ((rc = factor_inv_rec(h, A, lda, W, ldw, 0, size(0), logdiag, d_info, false, nullptr, 0))) return rc;
+    GPB_CU(cudaEventRecord(ev_start, S0), "pipeline start record");
+    GPB_CU(cudaStreamWaitEvent(M, ev_start, 0), "pipeline start wait");
+    GemmArgs g;
+    for (int k = 0; k < nb; ++k) {
+        const bool last = (k == nb - 1);
+        const int64_t rk = off(k);
+        const int nk = size(k);
+        cudaStream_t B = last ? S0 : M;
+        if (last && nb > 1) GPB_CU(cudaStreamWaitEvent(S0, ev_bulk, 0), "pipeline bulk join");
+        if (k > 0) GPB_CU(cudaStreamWaitEvent(B, evD(k), 0), "pipeline wait D");
+        double* Wkk = W + rk * ldw + rk;
+        if (!last) {
+            const int64_t r1 = off(k + 1), m1 = N - r1;
+            const int n1 = size(k + 1);
+            // P_k: T[k+1:, k] = A[k+1:, k] W_kk^T
+            g = GemmArgs();
+            g.transa = 0; g.transb = 1; g.M = m1; g.N = nk; g.K = nk;
+            g.A = A + r1 * lda + rk; g.lda = lda; g.B = Wkk; g.ldb = ldw; g.C = W + r1 * ldw + rk; g.ldc = ldw; g.b_upper = 1;
+            if ((rc = launch_gemm(h, g, M))) return rc;
+            // Sa_k: A[k+1:, block k+1] -= T[k+1:, k] T[k+1, k]^T
+            g = GemmArgs();
+            g.transa = 0; g.transb = 1; g.M = m1; g.N = n1; g.K = nk; g.alpha = -1.0; g.beta = 1.0;
+            g.A = W + r1 * ldw + rk; g.lda = ldw; g.B = W + r1 * ldw + rk; g.ldb = ldw; g.C = A + r1 * lda + r1; g.ldc = lda;
+            if ((rc = launch_gemm(h, g, M))) return rc;
+            GPB_CU(cudaEventRecord(evSa(k), M), "pipeline record Sa");
+            // D_k+1 in the small partition
+            GPB_CU(cudaStreamWaitEvent(C, evSa(k), 0), "pipeline wait Sa");
+            if (serial) {
+                rc = factor_inv_rec(h, A, lda, W, ldw, (int)r1, n1, logdiag, d_info, false, nullptr, 0);
+            } else {
+                StreamSwap swap(h, C, h->part_crit_side);
+                rc = factor_inv_rec(h, A, lda, W, ldw, (int)r1, n1, logdiag, d_info, false, nullptr, 0);
+            }
+            if (rc) return rc;
+            GPB_CU(cudaEventRecord(evD(k + 1), C), "pipeline record D");
+            // Sb_k: rest of the trailing update
+            if (k + 2 < nb) {
+                const int64_t r2 = off(k + 2), m2 = N - r2;
+                g = GemmArgs();
+                g.transa = 0; g.transb = 1; g.M = m2; g.N = m2; g.K = nk; g.alpha = -1.0; g.beta = 1.0;
+                g.A = W + r2 * ldw + rk; g.lda = ldw; g.B = g.A; g.ldb = ldw; g.C = A + r2 * lda + r2; g.ldc = lda; g.tri = 1;
+                if ((rc = launch_gemm(h, g, M))) return rc;
+            }
+        }
+        if (k > 0) {
+            // R_k: V = T[k, :k] W[:k, :k] -> A[k, :k];  W[k, :k] = -W_kk V
+            g = GemmArgs();
+            g.transa = 0; g.transb = 0; g.M = nk; g.N = rk; g.K = rk;
+            g.A = W + rk * ldw; g.lda = ldw; g.B = W; g.ldb = ldw; g.C = A + rk * lda; g.ldc = lda; g.b_lower = 1;
+            if ((rc = launch_gemm(h, g, B))) return rc;
+            g = GemmArgs();
+            g.transa = 0; g.transb = 0; g.M = nk; g.N = rk; g.K = nk; g.alpha = -1.0;
+            g.A = Wkk; g.lda = ldw; g.B = A + rk * lda; g.ldb = lda; g.C = W + rk * ldw; g.ldc = ldw; g.a_lower = 1;
+            if ((rc = launch_gemm(h, g, B))) return rc;
+        }
+        if (last) GPB_CU(cudaEventRecord(ev_W, B), "pipeline record W");
+        if (want_kinv) {
+            if (k > 0) {
+                // Q_k: K^-1[k, :k] = W_kk^T W[k, :k] ;  K^-1[:k, :k] += W[k, :k]^T W[k, :k]
+                g = GemmArgs();
+                g.transa = 1; g.transb = 0; g.M = nk; g.N = rk; g.K = nk;
+                g.A = Wkk; g.lda = ldw; g.B = W + rk * ldw; g.ldb = ldw; g.C = A + rk * lda; g.ldc = lda; g.a_upper = 1;
+                if ((rc = launch_gemm(h, g, B))) return rc;
+                g = GemmArgs();
+                g.transa = 1; g.transb = 0; g.M = rk; g.N = rk; g.K = nk; g.beta = 1.0;
+                g.A = W + rk * ldw; g.lda = ldw; g.B = g.A; g.ldb = ldw; g.C = A; g.ldc = lda; g.tri = 1;
+                if ((rc = launch_gemm(h, g, B))) return rc;
+            }
+            // K^-1[k, k] = W_kk^T W_kk (lower tiles)
+            g = GemmArgs();
+            g.transa = 1; g.transb = 0; g.M = nk; g.N = nk; g.K = nk;
+            g.A = Wkk; g.lda = ldw; g.B = Wkk; g.ldb = ldw; g.C = A + rk * lda + rk; g.ldc = lda; g.tri = 1; g.a_upper = 1;
+            if ((rc = launch_gemm(h, g, B))) return rc;
+        }
+        if (k == nb - 2) GPB_CU(cudaEventRecord(ev_bulk, M), "pipeline record bulk");
+    }
+    // the small partition's side streams joined their forks inside the recursion; its main stream ends at D_nb-1,
+    // which the last step waited for
+    (void)ev_crit;
+#undef GPB_CU
+    if (ev_W_ready) *ev_W_ready = ev_W;
+    return 0;
 }
 
 int lauum_lower(gpb_handle* h, const double* d_W, int64_t N, int64_t ldw, double* d_Out, int64_t ldo) {

@@ -36,6 +36,15 @@ struct gpb_handle {
     gpb_kernel_spec fact_spec = {};
     int64_t launches = 0;
     int sm_count = 148;
+    // SM partitions (green contexts, partition.cu) for the pipelined factorisation: streams of the bulk
+    // partition and of the small critical-chain partition; gpb_set_option(h, 4, x) switches the pipeline
+    bool part_ok = false;
+    bool use_pipeline = false;  // measured slower than the recursion (profiles/r02_pipeline_ab.txt): opt-in
+    cudaStream_t part_bulk = nullptr, part_crit = nullptr;
+    cudaStream_t part_crit_side[MAX_DEPTH] = {};
+    void* part_ctx[2] = {nullptr, nullptr};
+    int part_crit_sms = 0, part_bulk_sms = 0;
+    std::vector<cudaEvent_t> part_events;
 
     bool has_spec = false;
     gpb_kernel_spec spec;
@@ -167,12 +176,22 @@ inline cudaError_t ensure_dyn_smem(bool (&done)[GPB_MAX_DEVICES], int device, K 
     return e;
 }
 
+// ---- partition.cu
+void partitions_create(gpb_handle* h);
+void partitions_destroy(gpb_handle* h);
+cudaEvent_t partition_event(gpb_handle* h, size_t i);
+
 // ---- cholesky.cu
 // A (lower, in place) -> L on the diagonal blocks (and everywhere when keepL), W = L^-1 (lower, zero
 // strict-upper inside 128-aligned diagonal blocks), logdiag[b] = sum of log L_ii over block b,
 // *d_info = 1-based index of the first non-positive pivot (0 = ok).
 int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag, int* d_info,
                bool keepL);
+// Pipelined variant over the two SM partitions (see cholesky.cu); A ends as K^-1 (lower tiles) when want_kinv.
+// *ev_W_ready (optional) is recorded on the caller's stream when W is complete (before the last K^-1 products).
+bool pipeline_applies(const gpb_handle* h, int64_t N);
+int factor_inv_pipelined(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag,
+                         int* d_info, bool want_kinv, cudaEvent_t* ev_W_ready);
 // Factor only (N^3/3): L's diagonal NBD-blocks in A, the rest in Lw, block inverses in the [N, NBD] strip Wd.
 int factor_L(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, double* Wd, int64_t N, double* logdiag,
              int* d_info);

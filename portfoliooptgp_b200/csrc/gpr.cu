@@ -184,7 +184,26 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
     if ((rc = gpr_workspaces(h, &w))) return rc;
     const int P = kp.n_params;
     const bool refine = refine_objective(h, kp, noise);
-    if (want_grad && h->fork_streams && h->side[0]) {
+    if (want_grad && pipeline_applies(h, h->N) && h->side[0]) {
+        // large N: right-looking pipeline over the two SM partitions; K^-1 accumulates row block by row block
+        // inside it, the vector kernels start as soon as W is complete (beside the last K^-1 products)
+        if ((rc = launch_assemble(h, kp, h->d_X, h->N, h->d_X, h->N, h->D, w.A, w.ld, 1, noise))) return rc;
+        cudaEvent_t ev_W = nullptr;
+        if ((rc = factor_inv_pipelined(h, w.A, w.ld, w.W, w.ld, h->N, w.logdiag, w.info, true, &ev_W))) return rc;
+        cudaStream_t main_stream = h->stream, side = h->side[0];
+        cudaError_t e = cudaStreamWaitEvent(side, ev_W, 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "gpr pipeline fork");
+        h->stream = side;
+        rc = gpr_factor_vectors(h, w);
+        if (!rc && refine) rc = gpr_refine_objective(h, kp, noise, w, 1);
+        h->stream = main_stream;
+        if (rc) return rc;
+        e = cudaEventRecord(h->ev_join[0], side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, h->ev_join[0], 0);
+        if (e != cudaSuccess) return check_cuda(h, e, "gpr pipeline join");
+        factor_remember(h, theta, noise, 1);   // (a failed pivot invalidates it again below)
+        if ((rc = launch_grad_reduce(h, kp, h->d_X, h->N, h->D, w.A, w.ld, w.alpha, w.res + 2))) return rc;
+    } else if (want_grad && h->fork_streams && h->side[0]) {
         // the vector kernels (a, alpha, |a|^2, log-det) need W only, as does K^-1 = W^T W: they run on a side
         // stream beside the big product and meet again in front of the gradient reduction (which needs both)
         if ((rc = gpr_factor_matrix(h, kp, noise, w))) return rc;

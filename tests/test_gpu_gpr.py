@@ -285,3 +285,43 @@ def test_factor_only_flows_match_the_full_inverse_flows(gp, N):
     n0 = eng.launch_count()
     m2.predict_f(Xs)
     assert n_reuse < eng.launch_count() - n0                   # the reuse skipped assembly and factorisation
+
+
+@pytest.mark.parametrize("N", [3072, 3500, 5000])
+def test_pipelined_factorisation_matches_the_recursion_and_the_oracle(gp, N):
+    """Option 4 = 1, N >= 3072: objective + gradient run the right-looking pipeline over the two SM partitions
+    (csrc/cholesky.cu factor_inv_pipelined); the default is the single-partition recursion.  Both against
+    the oracle at the north-star bars, and a prediction from the factorisation the pipeline leaves behind."""
+    X, Y = make_multi_input(81, N, 8)
+    Xs, _ = make_multi_input(82, 200, 8)
+    k = gp.kernels.SquaredExponential(lengthscales=1.3) + gp.kernels.Matern52(variance=0.7, lengthscales=2.0) + gp.kernels.Linear(variance=0.2)
+    noise = 1e-2
+    ko = to_oracle(k)
+    l0, g0, n0 = O.gpr_lml_and_grad(ko, X, Y, noise)
+    m0, v0 = O.gpr_predict_f(ko, X, Y, noise, Xs)
+    m = gp.models.GPR((X, Y), kernel=k, noise_variance=noise)
+    eng = m._get_engine()
+    out = {}
+    for mode in (1, 0):
+        eng.set_option(eng.OPTION_PIPELINE, mode)
+        try:
+            lml, g, gn = m.lml_and_constrained_grads()
+            mean, var = m.predict_f(Xs)
+        finally:
+            eng.set_option(eng.OPTION_PIPELINE, 0)
+        gscale = max(1.0, np.max(np.abs(g0)), abs(n0))
+        assert abs(lml - l0) <= 1e-9 * abs(l0), (mode, lml, l0)
+        assert max(np.max(np.abs(g - g0)), abs(gn - n0)) <= 1e-7 * gscale, mode
+        assert np.max(np.abs(mean.numpy() - m0)) <= 1e-9 * np.max(np.abs(m0)), mode
+        assert np.max(np.abs(var.numpy() - v0) / np.abs(v0)) <= 1e-8, mode
+        out[mode] = (lml, g)
+    assert abs(out[0][0] - out[1][0]) <= 1e-12 * abs(l0)
+    # with the stream forks off the same task list runs on one stream: same numbers, bit for bit
+    eng.set_option(eng.OPTION_FORK_STREAMS, 0)
+    eng.set_option(eng.OPTION_PIPELINE, 1)
+    try:
+        lml_s, g_s, _ = m.lml_and_constrained_grads()
+    finally:
+        eng.set_option(eng.OPTION_FORK_STREAMS, 1)
+        eng.set_option(eng.OPTION_PIPELINE, 0)
+    assert lml_s == out[1][0] and np.array_equal(g_s, out[1][1])
