@@ -67,9 +67,28 @@ def measured_peaks():
         fp = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))
         peaks["fp64_tflops"] = float(fp["fp64_dgemm_tflops"])
         peaks["fp64_source"] = "profiles/FP64_PEAKS.json (cuBLAS DGEMM 8192^3 measured on this pool; MEASURED_PEAKS.json has no fp64 entry)"
+        peaks["fp64_record"] = {k: fp[k] for k in ("fp64_dgemm_tflops", "fp64_dgemm_tflops_sustained", "fp64_dmma_pipe_tflops",
+                                                    "fp64_dfma_pipe_tflops", "cusolver_potrf_8192_ms", "clocks", "when") if k in fp}
     except Exception:
         pass
     return peaks
+
+
+def measure_fp64_peak_live(torch, seconds=1.0):
+    """cuBLAS DGEMM 8192^3 through torch.matmul, timed in THIS run (the FP64 roofline denominator next to the
+    stored one; a comparison point, never on the product path)."""
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best, t_end = 1e9, time.perf_counter() + seconds
+    while time.perf_counter() < t_end:
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
 class ClockSampler:
@@ -300,6 +319,10 @@ def run_gpu(args):
     syrk_ms = e0.elapsed_time(e1) / 5
     syrk_tf = float(n2) ** 3 / (syrk_ms * 1e-3) / 1e12     # n2^2 * K flop (lower triangle of a rank-K update)
     del Tm, A22
+    try:
+        fp64_live = measure_fp64_peak_live(torch)
+    except Exception:
+        fp64_live = None
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_dgemm_summary.json")))["per_step"]["traffic_bytes"]
@@ -313,7 +336,8 @@ def run_gpu(args):
     roofline = {"bound": "tensor", "kernel": "dgemm_kernel (DMMA.8x8x4): Cholesky trailing update + panel/inverse/K^-1 products",
                 "achieved": achieved_tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["fp64_tflops"],
                 "traffic": traffic, "traffic_note": "DRAM bytes of the 13 big launches of one step, ncu --set full (profiles/r01_ncu_full_dgemm_summary.json)",
-                "peak_source": peaks["fp64_source"],
+                "peak_source": peaks["fp64_source"], "peak_record": peaks.get("fp64_record"),
+                "peak_live_this_run": fp64_live, "frac_of_live_peak": (achieved_tf / fp64_live) if fp64_live else None,
                 "trailing_update": {"shape": "SYRK n=4096, K=4096, lower tiles", "ms": syrk_ms, "achieved": syrk_tf,
                                     "frac": syrk_tf / peaks["fp64_tflops"], "unit": "TFLOP/s"},
                 "launches_per_step": n_cat["gemm"] / prof_steps, "ms_per_step": gemm_ms_step,
@@ -363,6 +387,11 @@ def run_gpu(args):
             extras["c5_svgp"] = bench_c5(gpflow, torch, dist, world, rank, barrier, eng)
         except Exception as e:
             extras["c5_svgp"] = {"error": repr(e)}
+    if not args.no_extras and rank == 0 and world == 1:
+        try:
+            extras["c4_large_gp"] = bench_c4(gpflow, torch)
+        except Exception as e:
+            extras["c4_large_gp"] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -409,12 +438,17 @@ def bench_c1(gpflow, torch):
     Y = (r - r.mean()) / r.std()
     K = gpflow.kernels
     out = {}
+    # untimed warm-up of the whole call pattern (SciPy's L-BFGS-B, the predict workspaces) on a small model
+    mw = gpflow.models.GPR(data=(X[:200], Y[:200]), kernel=K.SquaredExponential() + K.Periodic(K.SquaredExponential()), noise_variance=1e-2)
+    gpflow.optimizers.Scipy().minimize(mw.training_loss, mw.trainable_variables, options=dict(maxiter=5))
+    mw.predict_f(X[:200])
     for tag, s2 in (("noise_1e-2", 1e-2), ("noise_1e-5_reference", 1e-5)):
         k = K.SquaredExponential() + K.Periodic(K.SquaredExponential())
         m = gpflow.models.GPR(data=(X, Y), kernel=k)
         m.likelihood.variance.assign(s2)
         gpflow.set_trainable(m.likelihood.variance, False)
         m.lml_and_constrained_grads()  # warm the workspaces
+        m.predict_f(X)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         try:
@@ -471,6 +505,30 @@ def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
     ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / iters
     full = gather_results(m._out[:, :1].contiguous(), total)   # the single collective of this path
     ok = bool(torch.isfinite(full).all().item())
+    parity = None
+    if rank == 0:
+        # a sample of this rank's GPs against the CPU oracle (same theta, same noise): LML and gradient
+        try:
+            from oracle import gpflow_oracle as O
+            O.set_distance_form("direct")
+            ko = O.Product([O.Leaf("exponential", active_dims=slice(0, D - 1)), O.Leaf("exponential", active_dims=slice(D - 1, D))])
+            outs = m._out.cpu().numpy()
+            worst_l, worst_g = 0.0, 0.0
+            for b in range(0, hi - lo, max(1, (hi - lo) // 8)):
+                O.set_theta(ko, m.theta[b])
+                l0, g0, n0 = O.gpr_lml_and_grad(ko, Xb[b], Yb[b][:, None], float(m.noise[b]))
+                ref = np.concatenate([g0, [n0]])
+                worst_l = max(worst_l, abs(outs[b, 0] - l0) / abs(l0))
+                got = np.concatenate([outs[b, 2:2 + len(g0)], [outs[b, 1]]])      # record: lml, d/dnoise, d/dtheta
+                worst_g = max(worst_g, float(np.max(np.abs(got - ref)) / max(1.0, np.max(np.abs(ref)))))
+            parity = {"sampled_gps": 8, "lml_max_rel_diff_vs_oracle": worst_l, "grad_max_rel_to_max_diff_vs_oracle": worst_g}
+        except Exception as e:
+            parity = {"error": repr(e)[:200]}
+        finally:
+            try:
+                O.set_distance_form("gram")
+            except Exception:
+                pass
     # full fits (BASELINE metric "batched GPs/s ... full fits"): every rank runs the lock-step L-BFGS-B
     # (maxiter = 100, trainable noise, the restart grid) over its shard; wall clock, max over ranks
     barrier()
@@ -480,14 +538,57 @@ def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
     fit_s = _max_over_ranks(torch, dist, world, fit_s)
     conv = float(np.mean([r.success for r in res]))
     nit = float(np.mean([r.nit for r in res]))
+    if world > 1:   # iterations and convergence over ALL ranks (rank 0 used to report its own shard only)
+        t = torch.tensor([sum(r.nit for r in res), sum(bool(r.success) for r in res), len(res)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        nit, conv = float(t[0] / t[2]), float(t[1] / t[2])
     # algorithmic work per GP per eval: N^3 + ~60 N^2 flop
     flops = total * (N ** 3 + 60.0 * N ** 2)
     return {"workload": "C3: 5120 GPs (20x64x4), N=128, D=8, Exponential*Exponential, LML+grad, one GP per CTA",
             "gp_evals_per_s": total / (ms * 1e-3), "ms_per_batched_eval": ms, "gps_total": total, "gps_per_rank": hi - lo,
             "n_gpus": world, "gflops_algorithmic": flops / (ms * 1e-3) / 1e9, "gathered_finite": ok,
             "full_fits_per_s": total / fit_s, "full_fit_s": fit_s, "fit_mean_iterations": nit,
-            "fit_converged_fraction_rank0": conv,
+            "fit_converged_fraction": conv, "parity_sample": parity,
             "fit_note": "lock-step SciPy L-BFGS-B on the host (bit-identical iterates), LML+grad on the device"}
+
+
+def bench_c4(gpflow, torch):
+    """BASELINE config C4: N = 65536, D = 4 (3 return columns + time), SE + Matern52, noise 1e-2, fixed theta:
+    the value (factor only), predict_f at 16384 held-out points (cold and from the stored factor) and
+    value + gradient, each timed once with CUDA events after a small warm-up of the same code path."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120e9:
+        return {"skipped": "needs ~110 GB of free HBM, %.0f GB free" % (free / 1e9)}
+    N, Ns, D = 65536, 16384, 4
+    X, Y = make_c2(seed=4, n=N + Ns, d=D)
+    perm = np.random.default_rng(4).permutation(N + Ns)
+    Xtr, Ytr, Xte = X[perm[:N]], Y[perm[:N]], X[perm[N:]]
+    K = gpflow.kernels
+    k = K.SquaredExponential(lengthscales=1.5) + K.Matern52(variance=0.5, lengthscales=3.0)
+    warm = gpflow.models.GPR((Xtr[:4096], Ytr[:4096]), kernel=k, noise_variance=1e-2)
+    warm.predict_f(Xte[:256]); warm.lml_and_constrained_grads()
+    m = gpflow.models.GPR((Xtr, Ytr), kernel=k, noise_variance=1e-2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(f):
+        torch.cuda.synchronize(); e0.record(); r = f(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, r
+
+    out = {"workload": "C4: exact GP N=65536, D=4, SE+Matern52, noise 1e-2; predict_f at 16384 points", "N": N, "Ns": Ns}
+    out["lml_value_s"], lml = timed(lambda: float(m.log_marginal_likelihood()))
+    out["predict_f_from_stored_factor_s"], (mean, var) = timed(lambda: m.predict_f(Xte))
+    m._fact = None
+    out["predict_f_cold_s"], _ = timed(lambda: m.predict_f(Xte))
+    out["lml_grad_s"], (lml2, g, gn) = timed(lambda: m.lml_and_constrained_grads())
+    out["lml"] = lml
+    out["lml_value_vs_grad_path_rel_diff"] = abs(lml - lml2) / abs(lml)
+    out["factor_only_tflops"] = (float(N) ** 3 / 3) / out["lml_value_s"] / 1e12
+    out["lml_grad_tflops"] = float(N) ** 3 / out["lml_grad_s"] / 1e12
+    out["solve_tflops"] = float(N) ** 2 * Ns / out["predict_f_from_stored_factor_s"] / 1e12
+    out["parity"] = "tests/test_gpu_baseline_sizes.py: N=16384 vs the CPU oracle, N=65536 vs a cuSOLVER/cuBLAS block Cholesky"
+    del m
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_c5(gpflow, torch, dist, world, rank, barrier, eng, steps=3):
@@ -495,7 +596,7 @@ def bench_c5(gpflow, torch, dist, world, rank, barrier, eng, steps=3):
     data-parallel with one all-reduce of the flat gradient record per step."""
     from portfoliooptgp_b200.svgp_dp import SVGPDataParallel
     M, B, D, N = 2048, 65536, 8, 16 * 2 ** 20
-    shard_rows = min(N // world, 4 * B)   # resident window of this rank's shard (synthetic rows)
+    shard_rows = N // world               # this rank's whole shard of the 16 M synthetic rows is resident (1.2 GB at world = 1)
     g = torch.Generator(device="cuda"); g.manual_seed(5 + rank)
     X = torch.randn((shard_rows, D), dtype=torch.float64, device="cuda", generator=g)
     w = torch.randn((D, 1), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
@@ -518,7 +619,29 @@ def bench_c5(gpflow, torch, dist, world, rank, barrier, eng, steps=3):
     eng.profile_enable(False)
     flops = 6.0 * M * M * B
     peaks = measured_peaks()
-    return {"workload": "C5: SVGP M=2048, minibatch 65536/GPU, D=8, SquaredExponential, ELBO+grad+Adam step, data-parallel",
+    parity = None
+    if rank == 0:
+        # the engine's ELBO at the trainer's current parameters on a 2048-row sample against the CPU oracle
+        try:
+            from oracle import gpflow_oracle as O
+            O.set_distance_form("direct")
+            ns = 2048
+            Xs_, ys_ = tr.X[:ns].cpu().numpy(), tr.y[:ns].cpu().numpy()[:, None]
+            Zh, qm, qs = tr.Z.cpu().numpy(), tr.q_mu.cpu().numpy()[:, None], tr.q_sqrt.cpu().numpy()[None]
+            mdl = gpflow.models.SVGP(kernel=gpflow.kernels.SquaredExponential(variance=float(tr.theta[1]), lengthscales=float(tr.theta[0])),
+                                     likelihood=gpflow.likelihoods.Gaussian(variance=tr.noise), inducing_variable=Zh, num_data=N,
+                                     q_mu=qm, q_sqrt=qs)
+            got = float(mdl.elbo((Xs_, ys_)))
+            want = O.svgp_elbo(O.Leaf("se", float(tr.theta[1]), float(tr.theta[0])), Zh, qm, qs, tr.noise, Xs_, ys_, num_data=N)
+            parity = {"rows": ns, "elbo_rel_diff_vs_oracle": abs(got - want) / abs(want)}
+        except Exception as e:
+            parity = {"error": repr(e)[:200]}
+        finally:
+            try:
+                O.set_distance_form("gram")
+            except Exception:
+                pass
+    return {"parity_sample": parity, "shard_rows": shard_rows, "workload": "C5: SVGP M=2048, minibatch 65536/GPU, D=8, SquaredExponential, ELBO+grad+Adam step, data-parallel",
             "steps_per_s": 1e3 / ms, "ms_per_step": ms, "rows_per_s": world * B / (ms * 1e-3), "n_gpus": world,
             "allreduce_doubles": int(tr.flat.numel()), "elbo": elbo,
             "gemm_ms": ms_cat["gemm"], "gemm_tflops_algorithmic": flops / (ms_cat["gemm"] * 1e-3) / 1e12,

@@ -277,6 +277,20 @@ int gpb_prep_zscore(gpb_handle* h, const double* d_x, int64_t T, int64_t A, int 
 int gpb_prep_windows(gpb_handle* h, const double* d_feat, const double* d_y, int64_t S, int64_t T, int D,
                      int64_t N, int64_t stride, double* d_X, double* d_Y);
 
+/* ---- prediction post-processing (the step right after predict_f) -----------------------
+ * Replaces Predictor.upsample_predictions (/root/reference GPR/predictor.py:35-51):
+ * pd.Series(pred, index=X).reindex(X_daily).interpolate('linear') for Q prediction columns at once
+ * (d_pred [Q, Ns] -> d_out [Q, Nd]): exact-value lookup of the sparse points in the daily grid, linear
+ * interpolation over daily POSITIONS, NaN before the first matched point, last value repeated after
+ * the last.  d_Xdaily [Nd] and d_X [Ns] ascending and unique.  Bit-identical to pandas. */
+int gpb_post_upsample(gpb_handle* h, const double* d_Xdaily, int64_t Nd, const double* d_X, int64_t Ns,
+                      const double* d_pred, int Q, double* d_out);
+/* Replaces the blend of Predictor.predict_combined (GPR/predictor.py:27-31):
+ * d_out = alpha * daily + beta * weekly + (1 - alpha - beta) * monthly over n values (all four columns
+ * of predict_single may be passed as one [4 n] array), the reference's evaluation order. */
+int gpb_post_blend(gpb_handle* h, double alpha, double beta, const double* d_daily, const double* d_weekly,
+                   const double* d_monthly, int64_t n, double* d_out);
+
 #ifdef __cplusplus
 }
 #endif

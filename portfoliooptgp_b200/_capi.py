@@ -101,6 +101,8 @@ SIGNATURES = {
     "gpb_prep_returns": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P]),
     "gpb_prep_zscore": (_INT, [_P, _P, _I64, _I64, _INT, _P, _I64, _P, _P]),
     "gpb_prep_windows": (_INT, [_P, _P, _P, _I64, _I64, _INT, _I64, _I64, _P, _P]),
+    "gpb_post_upsample": (_INT, [_P, _P, _I64, _P, _I64, _P, _INT, _P]),
+    "gpb_post_blend": (_INT, [_P, _D, _D, _P, _P, _P, _I64, _P]),
 }
 
 
@@ -316,6 +318,13 @@ class Engine:
     def prep_windows(self, dfeat: int, dy: int, S: int, T: int, D: int, N: int, stride: int, dX: int, dY: int):
         self._check(self._lib.gpb_prep_windows(self._h, _P(dfeat), _P(dy), S, T, D, N, stride, _P(dX), _P(dY)),
                     "gpb_prep_windows")
+
+    def post_upsample(self, dXd: int, Nd: int, dXs: int, Ns: int, dpred: int, Q: int, dout: int):
+        self._check(self._lib.gpb_post_upsample(self._h, _P(dXd), Nd, _P(dXs), Ns, _P(dpred), Q, _P(dout)), "gpb_post_upsample")
+
+    def post_blend(self, alpha: float, beta: float, dd: int, dw: int, dm: int, n: int, dout: int):
+        self._check(self._lib.gpb_post_blend(self._h, float(alpha), float(beta), _P(dd), _P(dw), _P(dm), n, _P(dout)),
+                    "gpb_post_blend")
 
     def gpr_factor_serial(self) -> int:
         return int(self._lib.gpb_gpr_factor_serial(self._h))

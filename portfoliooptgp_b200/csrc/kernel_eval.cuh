@@ -150,13 +150,14 @@ struct DynShape {
 };
 
 // G* = group kind (-1: unused); L* = leaf kind | group << 4 (-1: unused);
-// T* = n_factors | leaf0 << 4 | leaf1 << 8 | leaf2 << 12 | leaf3 << 16 (0: unused).  At most 2 groups, 4
-// leaves (the register-resident gradient path), 4 terms.
-template <int G0, int G1, int L0, int L1, int L2, int L3, int T0, int T1, int T2, int T3>
+// T* = n_factors | leaf0 << 4 | leaf1 << 8 | leaf2 << 12 | leaf3 << 16 (0: unused).  At most 3 groups (the
+// third one, G2, is the trailing template argument), 4 leaves (the register-resident gradient path), 4 terms.
+template <int G0, int G1, int L0, int L1, int L2, int L3, int T0, int T1, int T2, int T3, int G2 = -1>
 struct StaticShape {
     static constexpr bool is_static = true;
     static constexpr bool UNIT_W = false;   // see UnitWeights below
-    static constexpr int NG = (G0 >= 0) + (G1 >= 0);
+    static constexpr int NG = (G0 >= 0) + (G1 >= 0) + (G2 >= 0);
+    static __host__ __device__ constexpr int gcode(int g) { return g == 0 ? G0 : g == 1 ? G1 : G2; }
     static constexpr int NL = (L0 >= 0) + (L1 >= 0) + (L2 >= 0) + (L3 >= 0);
     static constexpr int NT = (T0 != 0) + (T1 != 0) + (T2 != 0) + (T3 != 0);
     static __host__ __device__ constexpr int lcode(int l) { return l == 0 ? L0 : l == 1 ? L1 : l == 2 ? L2 : L3; }
@@ -176,12 +177,12 @@ struct StaticShape {
                                    pure_exp(L0) && pure_exp(L1) && G0 == GPB_GROUP_EUCLID &&
                                    (G1 < 0 || G1 == GPB_GROUP_EUCLID);
     static __host__ __device__ constexpr int n_groups(const DevKernel&) { return NG; }
-    static __host__ __device__ constexpr int group_kind(const DevKernel&, int g) { return g == 0 ? G0 : G1; }
+    static __host__ __device__ constexpr int group_kind(const DevKernel&, int g) { return gcode(g); }
     static __host__ __device__ constexpr int n_leaves(const DevKernel&) { return NL; }
     static __host__ __device__ constexpr int leaf_kind(const DevKernel&, int l) { return lcode(l) & 15; }
     static __host__ __device__ constexpr int leaf_group(const DevKernel&, int l) { return (lcode(l) >> 4) & 15; }
     static __host__ __device__ constexpr int leaf_arg_is_r(const DevKernel&, int l) {
-        return (((lcode(l) >> 4) & 15) == 0 ? G0 : G1) == GPB_GROUP_PERIODIC_ABS ? 1 : 0;
+        return gcode((lcode(l) >> 4) & 15) == GPB_GROUP_PERIODIC_ABS ? 1 : 0;
     }
     static __host__ __device__ constexpr int n_terms(const DevKernel&) { return NT; }
     static __host__ __device__ constexpr int term_nf(const DevKernel&, int t) { return tcode(t) & 15; }

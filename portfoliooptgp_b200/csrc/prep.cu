@@ -183,9 +183,100 @@ int prep_windows(gpb_handle* h, const double* d_feat, const double* d_y, int64_t
     return check_cuda(h, cudaGetLastError(), "window_gather_kernel launch");
 }
 
+// ---- prediction post-processing (GPR/predictor.py:10-51) -----------------------------------------
+// upsample_predictions: pd.Series(pred, index=X).reindex(X_daily).interpolate('linear') -- exact-value lookup of
+// the sparse (weekly / monthly) points in the daily grid, then linear interpolation over POSITIONS in the
+// daily grid (pandas ignores the index values), NaN before the first matched point, the last value repeated
+// after the last one.  Both grids ascending and unique (dates).  One thread per daily position: binary search
+// for its bracketing sparse points, skipping sparse values that are not on the daily grid; Q prediction
+// columns (f_mean, f_var, y_mean, y_var) share the search.  The interpolation is numpy's
+// slope * (x - x_lo) + y_lo with separately rounded operations, so the result is bit-identical to pandas.
+// HBM-bound byte mover: 8 (1 + Q) bytes per daily position out/in plus the (L2-resident) sparse series.
+__device__ __forceinline__ int64_t lower_bound_d(const double* __restrict__ a, int64_t n, double v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void post_upsample_kernel(const double* __restrict__ Xd, int64_t Nd, const double* __restrict__ Xs, int64_t Ns,
+                                     const double* __restrict__ pred, int Q, double* __restrict__ out) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < Nd; j += (int64_t)gridDim.x * blockDim.x) {
+        const double x = Xd[j];
+        // sparse points on the grid at or before / at or after daily position j
+        int64_t i_hi = lower_bound_d(Xs, Ns, x), p_hi = -1;
+        int64_t i_lo = (i_hi < Ns && Xs[i_hi] == x) ? i_hi : i_hi - 1, p_lo = -1;
+        for (; i_lo >= 0; --i_lo) {          // (skips sparse values that are not daily grid values)
+            const int64_t p = lower_bound_d(Xd, Nd, Xs[i_lo]);
+            if (p < Nd && Xd[p] == Xs[i_lo]) { p_lo = p; break; }
+        }
+        for (; i_hi < Ns; ++i_hi) {
+            const int64_t p = lower_bound_d(Xd, Nd, Xs[i_hi]);
+            if (p < Nd && Xd[p] == Xs[i_hi]) { p_hi = p; break; }
+        }
+        for (int q = 0; q < Q; ++q) {
+            const double* pq = pred + (int64_t)q * Ns;
+            double v;
+            if (p_lo < 0) v = nan;                               // before the first matched point
+            else if (p_hi < 0 || p_hi == p_lo) v = pq[i_lo];     // after the last one, or on a matched point
+            else {
+                const double slope = __ddiv_rn(__dsub_rn(pq[i_hi], pq[i_lo]), (double)(p_hi - p_lo));
+                v = __dadd_rn(__dmul_rn(slope, (double)(j - p_lo)), pq[i_lo]);
+            }
+            out[(int64_t)q * Nd + j] = v;
+        }
+    }
+}
+
+// out = alpha * daily + beta * weekly + (1 - alpha - beta) * monthly, in the reference's evaluation order
+// (GPR/predictor.py:27-31), separately rounded: bit-identical to the NumPy expression.
+__global__ void post_blend_kernel(double alpha, double beta, const double* __restrict__ d, const double* __restrict__ w,
+                                  const double* __restrict__ m, int64_t n, double* __restrict__ out) {
+    const double gamma = __dsub_rn(__dsub_rn(1.0, alpha), beta);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __dadd_rn(__dadd_rn(__dmul_rn(alpha, d[i]), __dmul_rn(beta, w[i])), __dmul_rn(gamma, m[i]));
+}
+
+int post_upsample(gpb_handle* h, const double* d_Xd, int64_t Nd, const double* d_Xs, int64_t Ns, const double* d_pred, int Q,
+                  double* d_out) {
+    if (Nd == 0) return 0;
+    post_upsample_kernel<<<flat_grid(h, Nd, 256), 256, 0, h->stream>>>(d_Xd, Nd, d_Xs, Ns, d_pred, Q, d_out);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "post_upsample_kernel launch");
+}
+
+int post_blend(gpb_handle* h, double alpha, double beta, const double* d_d, const double* d_w, const double* d_m, int64_t n,
+               double* d_out) {
+    if (n == 0) return 0;
+    post_blend_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(alpha, beta, d_d, d_w, d_m, n, d_out);
+    h->launches += 1;
+    return check_cuda(h, cudaGetLastError(), "post_blend_kernel launch");
+}
+
 }  // namespace gpb
 
 extern "C" {
+
+int gpb_post_upsample(gpb_handle* h, const double* d_Xdaily, int64_t Nd, const double* d_X, int64_t Ns, const double* d_pred,
+                      int Q, double* d_out) {
+    GPB_ENTER(h);
+    if (Nd < 0 || Ns < 0 || Q < 1) return gpb::set_error(h, -2, "post_upsample: bad sizes");
+    if (Nd > 0 && (!d_Xdaily || !d_out)) return gpb::set_error(h, -2, "post_upsample: null pointer");
+    if (Ns > 0 && (!d_X || !d_pred)) return gpb::set_error(h, -2, "post_upsample: null pointer");
+    return gpb::post_upsample(h, d_Xdaily, Nd, d_X, Ns, d_pred, Q, d_out);
+}
+
+int gpb_post_blend(gpb_handle* h, double alpha, double beta, const double* d_daily, const double* d_weekly,
+                   const double* d_monthly, int64_t n, double* d_out) {
+    GPB_ENTER(h);
+    if (n < 0) return gpb::set_error(h, -2, "post_blend: negative size");
+    if (n > 0 && (!d_daily || !d_weekly || !d_monthly || !d_out)) return gpb::set_error(h, -2, "post_blend: null pointer");
+    return gpb::post_blend(h, alpha, beta, d_daily, d_weekly, d_monthly, n, d_out);
+}
 
 int gpb_prep_returns(gpb_handle* h, const double* d_close, const double* d_open, int64_t T, int64_t A, int kind,
                      double* d_out) {

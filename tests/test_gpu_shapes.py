@@ -25,8 +25,9 @@ def _shapes(gp, D):
         "se+m52": (9, K.SquaredExponential(lengthscales=1.1) + K.Matern52(variance=0.6, lengthscales=1.7)),
         "se+per(se)": (10, K.SquaredExponential(lengthscales=1.3) + K.Periodic(K.SquaredExponential(variance=0.5, lengthscales=0.9, active_dims=last), period=1.9)),
         "exp+per(se)": (11, K.Exponential(lengthscales=1.3) + K.Periodic(K.SquaredExponential(variance=0.5, lengthscales=0.9, active_dims=last), period=1.9)),
+        # three groups (GPR/main.py:111)
+        "exp+per(se)+lin": (12, K.Exponential(lengthscales=1.3) + K.Periodic(K.SquaredExponential(active_dims=last), period=1.9) + K.Linear(variance=0.3)),
         # not in the table: stays on the interpreter
-        "exp+per(se)+lin": (0, K.Exponential(lengthscales=1.3) + K.Periodic(K.SquaredExponential(active_dims=last), period=1.9) + K.Linear(variance=0.3)),
         "m32": (0, K.Matern32(lengthscales=1.1)),
     }
     if D >= 2:
@@ -114,3 +115,19 @@ def test_svgp_and_sgpr_equivalence(gp, restore_option):
         assert a[2] == pytest.approx(b[2], rel=1e-12), name
         np.testing.assert_allclose(a[1], b[1], rtol=1e-9, atol=1e-9 * np.max(np.abs(b[1])), err_msg=name)
         np.testing.assert_allclose(a[3], b[3], rtol=1e-9, atol=1e-9 * np.max(np.abs(b[3])), err_msg=name)
+
+
+def test_every_reference_candidate_has_a_straight_line_shape(gp):
+    """The 8 kernel candidates of GPR/main.py:105-114 at the reference's D = 1: none of them runs on the
+    interpreter (gpb_kernel_shape != 0), VERDICT r01 missing #8."""
+    from portfoliooptgp_b200.kernels import compile_kernel
+    K = gp.kernels
+    cands = [K.SquaredExponential(), K.Matern12(), K.RationalQuadratic(), K.Exponential(), K.SquaredExponential() + K.Matern12(),
+             K.Exponential() + K.Periodic(K.SquaredExponential()) + K.Linear(), K.Exponential() + K.Periodic(K.SquaredExponential()),
+             K.SquaredExponential() * K.Matern12()]
+    eng = _engine(gp)
+    ids = []
+    for k in cands:
+        eng.set_kernel(compile_kernel(k, 1).spec)
+        ids.append(eng.kernel_shape())
+    assert all(i != 0 for i in ids) and len(set(ids)) == 8, ids

@@ -131,3 +131,23 @@ def test_data_parallel_trainer_single_rank(gp):
     vals = [tr.step() for _ in range(40)]
     assert np.mean(vals[-4:]) > first + 100.0
     assert np.allclose(np.triu(tr.q_sqrt.cpu().numpy(), 1), 0.0)
+
+
+def test_data_parallel_trainer_trains_the_noise_when_asked(gp):
+    """GPflow's likelihood variance is trainable by default; the trainer keeps it frozen unless
+    train_noise=True (the reference freezes it, test_scripts/SVGP.py:524).  With train_noise the variance
+    moves (through the softplus + 1e-6 transform) and the ELBO improves faster than with it frozen."""
+    from portfoliooptgp_b200.svgp_dp import SVGPDataParallel
+    X, Y = make_multi_input(92, 4096, 4)
+    Z = X[:64].copy()
+    runs = {}
+    for train_noise in (False, True):
+        k = gp.kernels.SquaredExponential(lengthscales=1.5)
+        # the targets are z-scored (variance 1): a likelihood variance of 4 is far too large
+        tr = SVGPDataParallel(k, 4.0, Z, num_data=4096, X_shard=X, Y_shard=Y, minibatch_size=1024, lr=5e-2,
+                              train_noise=train_noise, seed=3)
+        vals = [tr.step() for _ in range(80)]
+        runs[train_noise] = (tr.noise, float(np.mean(vals[-4:])))
+    assert runs[False][0] == 4.0
+    assert 1e-6 < runs[True][0] < 2.5
+    assert runs[True][1] > runs[False][1]

@@ -55,3 +55,60 @@ def test_data_parallel_elbo_reduction_gloo_world2():
     for _, elbo, tag in outs:
         assert abs(elbo - want) <= 1e-12 * abs(want)
         assert tag == 3.0
+
+
+def test_shard_windows_visit_every_row_and_keep_rows_paired():
+    """the window cursor used to reset at the end of the shard, so the last n mod B rows were never
+    drawn.  With the per-epoch permutation every row is drawn equally often, and X rows stay with their targets."""
+    import torch
+    from portfoliooptgp_b200.svgp_dp import ShardWindows
+    n, B = 10, 4
+    X = torch.arange(n, dtype=torch.float64)[:, None].repeat(1, 3)
+    y = 100.0 + torch.arange(n, dtype=torch.float64)
+    w = ShardWindows(X, y, B, seed=1)
+    counts = np.zeros(n)
+    for _ in range(4000):
+        o = w.next()
+        xb, yb = X[o:o + B], y[o:o + B]
+        assert torch.equal(xb[:, 0] + 100.0, yb) and torch.equal(xb[:, 0], xb[:, 2])
+        counts[xb[:, 0].long().numpy()] += 1
+    assert w.epoch > 1000
+    assert counts.min() > 0.85 * counts.mean() and counts.max() < 1.15 * counts.mean()
+    # without shuffling the old behaviour (fixed windows) is still available, explicitly
+    w2 = ShardWindows(X.clone(), y.clone(), B, shuffle=False)
+    assert [w2.next() for _ in range(4)] == [0, 4, 0, 4]
+
+
+def _worker_unequal(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from portfoliooptgp_b200.svgp_dp import check_equal_minibatch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        check_equal_minibatch(64, torch.device("cpu"))
+        ok_same = True
+        try:
+            check_equal_minibatch(64 + rank, torch.device("cpu"))
+            raised = False
+        except ValueError:
+            raised = True
+        q.put((rank, ok_same, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unequal_minibatch_sizes_are_rejected_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_unequal, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and raised for _, ok, raised in outs)
