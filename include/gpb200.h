@@ -208,6 +208,15 @@ int gpb_batched_lml_grad(gpb_handle* h, const double* d_X, const double* d_Yc, c
 int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
                           const double* d_noise, int64_t B, int64_t N, int D, const double* d_Xs,
                           int64_t Ns, double* d_mean, double* d_var, int32_t* d_info);
+/* Ragged variants: GP b uses only the first d_nrows[b] (1 <= d_nrows[b] <= Nmax) of its Nmax rows of
+ * d_X [B,Nmax,D] / d_Yc [B,Nmax] -- the reference's EXPANDING windows X_full[:i], i = i0, i0+1, ...
+ * (Multi-Input_GPR/main.py:414-423) as one batch, each GP with its own N.  Everything else as above. */
+int gpb_batched_lml_grad_ragged(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                                const double* d_noise, const int32_t* d_nrows, int64_t B, int64_t Nmax, int D,
+                                double* d_out, int32_t* d_info, int want_grad);
+int gpb_batched_predict_f_ragged(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                                 const double* d_noise, const int32_t* d_nrows, int64_t B, int64_t Nmax, int D,
+                                 const double* d_Xs, int64_t Ns, double* d_mean, double* d_var, int32_t* d_info);
 
 /* ---- SVGP (north_star subsystem 5) ---------------------------------------------------------------
  * Replaces gpflow.models.SVGP(kernel, Gaussian, Z, num_data).elbo / training_loss_closure /

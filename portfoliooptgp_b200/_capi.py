@@ -89,6 +89,8 @@ SIGNATURES = {
     "gpb_gpr_get_alpha": (_INT, [_P, _P]),
     "gpb_batched_lml_grad": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
     "gpb_batched_predict_f": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
+    "gpb_batched_lml_grad_ragged": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
+    "gpb_batched_predict_f_ragged": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
     "gpb_svgp_flat_size": (_I64, [_I64, _INT, _INT]),
     "gpb_svgp_data_term": (_INT, [_P, _DP, _D, _P, _I64, _INT, _P, _P, _I64, _P, _P, _I64, _P, _INT]),
     "gpb_svgp_finish": (_INT, [_P, _P, _D, _P, _P, _I64, _I64, _INT, _INT, _INT, _DP, _DP]),
@@ -256,14 +258,24 @@ class Engine:
 
     # -- batched small GPs -----------------------------------------------------------------------
     def batched_lml_grad(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dout: int,
-                         dinfo: int, want_grad: bool = True):
-        self._check(self._lib.gpb_batched_lml_grad(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dout),
-                                                   _P(dinfo), int(bool(want_grad))), "gpb_batched_lml_grad")
+                         dinfo: int, want_grad: bool = True, dnrows: Optional[int] = None):
+        if dnrows is None:
+            self._check(self._lib.gpb_batched_lml_grad(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dout),
+                                                       _P(dinfo), int(bool(want_grad))), "gpb_batched_lml_grad")
+        else:
+            self._check(self._lib.gpb_batched_lml_grad_ragged(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), _P(dnrows), B, N,
+                                                              D, _P(dout), _P(dinfo), int(bool(want_grad))),
+                        "gpb_batched_lml_grad_ragged")
 
     def batched_predict_f(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dXs: int, Ns: int,
-                          dmean: int, dvar: int, dinfo: int):
-        self._check(self._lib.gpb_batched_predict_f(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dXs),
-                                                    Ns, _P(dmean), _P(dvar), _P(dinfo)), "gpb_batched_predict_f")
+                          dmean: int, dvar: int, dinfo: int, dnrows: Optional[int] = None):
+        if dnrows is None:
+            self._check(self._lib.gpb_batched_predict_f(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), B, N, D, _P(dXs),
+                                                        Ns, _P(dmean), _P(dvar), _P(dinfo)), "gpb_batched_predict_f")
+        else:
+            self._check(self._lib.gpb_batched_predict_f_ragged(self._h, _P(dX), _P(dYc), _P(dtheta), _P(dnoise), _P(dnrows), B, N,
+                                                               D, _P(dXs), Ns, _P(dmean), _P(dvar), _P(dinfo)),
+                        "gpb_batched_predict_f_ragged")
 
     # -- SVGP ---------------------------------------------------------------------------------------
     def svgp_flat_size(self, M: int, D: int, P: int) -> int:

@@ -30,17 +30,47 @@ from .likelihoods import DEFAULT_VARIANCE_LOWER_BOUND
 # ---- lock-step L-BFGS-B ------------------------------------------------------------------------------
 
 
+_SCIPY_CHECKED = None
+
+
+def _scipy_lbfgsb_module():
+    """The lock-step driver re-drives SciPy's PRIVATE reverse-communication routine
+    (``scipy.optimize._lbfgsb_py._lbfgsb.setulb``, the C translation shipped since SciPy 1.15: integer
+    task / ln_task arrays, no csave / iprint).  Checked once; an older or changed SciPy gets a clear error
+    instead of a TypeError from the first fit (tested range: SciPy 1.15 - 1.18)."""
+    global _SCIPY_CHECKED
+    if _SCIPY_CHECKED is None:
+        from scipy.optimize import _lbfgsb_py as _lb
+        ver = tuple(int(v) for v in scipy.__version__.split(".")[:2] if v.isdigit())
+        missing = [a for a in ("_lbfgsb", "status_messages", "task_messages") if not hasattr(_lb, a)]
+        if not missing and not hasattr(_lb._lbfgsb, "setulb"):
+            missing.append("_lbfgsb.setulb")
+        if missing or ver < (1, 15):
+            raise RuntimeError(
+                f"portfoliooptgp_b200.batched needs SciPy >= 1.15 with the C L-BFGS-B driver (found SciPy {scipy.__version__}"
+                f"{', missing ' + ', '.join(missing) if missing else ''}); fit the GPs one by one with optimizers.Scipy instead")
+        _SCIPY_CHECKED = _lb
+    return _SCIPY_CHECKED
+
+
 def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]], X0: np.ndarray,
                     maxiter: int = 15000, maxfun: int = 15000, maxcor: int = 10, ftol: float = 2.2204460492503131e-09,
-                    gtol: float = 1e-5, maxls: int = 20, workers: int = 0) -> List[scipy.optimize.OptimizeResult]:
+                    gtol: float = 1e-5, maxls: int = 20, workers: int = 0,
+                    fun_batch_async: Optional[Callable] = None) -> List[scipy.optimize.OptimizeResult]:
     """Minimise B independent problems with SciPy's L-BFGS-B, advancing them in lock step.
 
     ``fun_batch(X [b, n], idx [b]) -> (f [b], g [b, n])`` evaluates the problems ``idx`` at ``X``.
     Each problem runs the reverse-communication loop of ``scipy.optimize._lbfgsb_py._minimize_lbfgsb``
     (same ``_lbfgsb.setulb``, same defaults, same stopping rules); whenever a problem asks for
     f and g it is parked until every active problem has asked, then one ``fun_batch`` call serves
-    them all."""
-    from scipy.optimize import _lbfgsb_py as _lb
+    them all.
+
+    ``fun_batch_async(X, idx) -> wait`` (optional; ``wait() -> (f, g)``) starts an evaluation without
+    blocking.  With it the problems are split into two halves that alternate: while the device evaluates
+    one half the host advances the other half's SciPy state machines, so device time, copies and launch
+    latency disappear behind the host loop.  The sequence of (x, f, g) every problem sees is unchanged, so
+    the iterates stay bit-identical to SciPy's."""
+    _lb = _scipy_lbfgsb_module()
     if workers and workers > 1 and len(X0) >= 4 * workers:
         return _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, int(workers))
     _lbfgsb = _lb._lbfgsb
@@ -81,37 +111,67 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     except Exception:  # pragma: no cover - threadpoolctl ships with scikit-learn; the loop works without it
         blas_single = None
 
+    def advance(group):
+        """run every problem of ``group`` until it needs f, g (returned) or stops"""
+        waiting = []
+        for b in group:
+            a = args[b]
+            task = a[11]
+            while True:
+                setulb(*a)
+                t0 = task[0]
+                if t0 == 3:
+                    waiting.append(b)
+                    break
+                elif t0 == 1:
+                    NIT[b] += 1
+                    if NIT[b] >= maxiter:
+                        task[0] = 5
+                        task[1] = 504
+                    elif NFEV[b] > maxfun:
+                        task[0] = 5
+                        task[1] = 502
+                else:
+                    break
+        return waiting
+
+    def scatter(idx, fb, gb):
+        F[idx] = np.asarray(fb, dtype=np.float64)
+        G[idx] = np.asarray(gb, dtype=np.float64)
+        NFEV[idx] += 1
+
     try:
-        active = list(range(B))
-        while active:
-            waiting = []
-            for b in active:
-                a = args[b]
-                task = a[11]
-                while True:  # advance until this problem needs f,g or stops
-                    setulb(*a)
-                    t0 = task[0]
-                    if t0 == 3:
-                        waiting.append(b)
-                        break
-                    elif t0 == 1:
-                        NIT[b] += 1
-                        if NIT[b] >= maxiter:
-                            task[0] = 5
-                            task[1] = 504
-                        elif NFEV[b] > maxfun:
-                            task[0] = 5
-                            task[1] = 502
-                    else:
-                        break
-            if not waiting:
-                break
-            idx = np.asarray(waiting, dtype=np.int64)
-            fb, gb = fun_batch(X[idx], idx)
-            F[idx] = np.asarray(fb, dtype=np.float64)
-            G[idx] = np.asarray(gb, dtype=np.float64)
-            NFEV[idx] += 1
-            active = waiting
+        if fun_batch_async is not None and B >= 2:
+            # two halves in flight: advance one on the host while the device evaluates the other
+            groups = [list(range(0, B // 2)), list(range(B // 2, B))]
+            pending = [None, None]
+            for h in (0, 1):
+                groups[h] = advance(groups[h])
+                if groups[h]:
+                    idx = np.asarray(groups[h], dtype=np.int64)
+                    pending[h] = (idx, fun_batch_async(X[idx], idx))
+            h = 0
+            while pending[0] is not None or pending[1] is not None:
+                if pending[h] is not None:
+                    idx, wait = pending[h]
+                    fb, gb = wait()
+                    scatter(idx, fb, gb)
+                    groups[h] = advance(groups[h])
+                    pending[h] = None
+                    if groups[h]:
+                        idx = np.asarray(groups[h], dtype=np.int64)
+                        pending[h] = (idx, fun_batch_async(X[idx], idx))
+                h ^= 1
+        else:
+            active = list(range(B))
+            while active:
+                waiting = advance(active)
+                if not waiting:
+                    break
+                idx = np.asarray(waiting, dtype=np.int64)
+                fb, gb = fun_batch(X[idx], idx)
+                scatter(idx, fb, gb)
+                active = waiting
     finally:
         if blas_single is not None:
             blas_single.restore_original_limits()
@@ -210,9 +270,18 @@ class BatchedGPR:
     X [B,N,D], Y [B,N] (or [B,N,1]); ``kernel`` gives the expression, the trainable flags and the
     initial hyper-parameters of every GP; ``noise_variance`` scalar or [B] (the restart grid of
     models/model_trainer.py:26 is a [B] vector); ``train_noise`` mirrors
-    ``set_trainable(model.likelihood, True/False)``."""
+    ``set_trainable(model.likelihood, True/False)``.
 
-    def __init__(self, X, Y, kernel: Kernel, noise_variance=1.0, train_noise: bool = True, device=None):
+    ``nrows`` [B] (optional): GP b is fitted on the first ``nrows[b]`` rows of ``X[b]`` only.  That is how
+    the reference's rolling re-fit maps onto one batch WITHOUT changing the model: its loop
+    (Multi-Input_GPR/main.py:414-456) fits EXPANDING windows ``X_full[:i]``, one more row per test day, so
+    ``X[b] = X_full[:Nmax]`` for every b and ``nrows = [i0, i0 + 1, ...]`` (``data_prep.expanding_windows``
+    builds exactly that) gives each GP the data the reference gives it.  ``data_prep.rolling_windows`` cuts
+    fixed-length SLIDING windows instead (BASELINE config C3): a different model from the reference's loop.
+    Windows longer than 128 rows do not fit one CTA's shared memory (a 128 x 132 fp64 tile is 135 of the
+    227 KB, and the inverse needs a second 35 KB tile); fit those with ``models.GPR``, one after the other."""
+
+    def __init__(self, X, Y, kernel: Kernel, noise_variance=1.0, train_noise: bool = True, device=None, nrows=None):
         self.device_index = ops.cuda_device_index(device)
         self.X = ops.to_device(X, self.device_index)
         if self.X.ndim != 3:
@@ -227,7 +296,15 @@ class BatchedGPR:
             raise ValueError("Y must be [B, N]")
         self.Y = Yd.contiguous()
         if self.N > 128:
-            raise ValueError("the one-GP-per-CTA path holds K in shared memory: N <= 128")
+            raise ValueError("the one-GP-per-CTA path holds K in shared memory: N <= 128 (use models.GPR for longer windows)")
+        self.nrows = None
+        self._nrows_dev = None
+        if nrows is not None:
+            nr = np.asarray(nrows, dtype=np.int32).reshape(-1)
+            if nr.shape[0] != self.B or nr.min() < 1 or nr.max() > self.N:
+                raise ValueError("nrows must be [B] with 1 <= nrows[b] <= N")
+            self.nrows = nr
+            self._nrows_dev = torch.from_numpy(nr).to(self.X.device)
         self.kernel = kernel
         self.compiled = compile_kernel(kernel, self.D)
         self.P = self.compiled.n_params
@@ -242,35 +319,60 @@ class BatchedGPR:
         self.trainable_mask = mask
         self._theta_tf = Softplus(0.0)
         self._noise_tf = Softplus(DEFAULT_VARIANCE_LOWER_BOUND)
+        self.non_pd_evaluations = np.zeros(self.B, dtype=np.int64)
         self._engine = ops.shared_engine(self.device_index)
         self._out = torch.empty((self.B, 2 + self.P), dtype=torch.float64, device=self.X.device)
         self._info = torch.zeros((self.B,), dtype=torch.int32, device=self.X.device)
+        # second result set for the pipelined fit (two half-batches in flight, lockstep_lbfgsb)
+        self._out2 = None
+        self._info2 = None
+        self._flip = 0
 
     # -- raw device evaluation ---------------------------------------------------------------------
-    def _launch(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool):
+    def _launch(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool, slot: int = 0):
         eng = self._engine
         ops.sync_stream(eng)
         eng.set_kernel(self.compiled.spec, self.compiled.token)
         dev = self.X.device
         th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev, non_blocking=True)
         nz = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev, non_blocking=True)
+        nr = self._nrows_dev
         if idx is None:
             Xb, Yb, b = self.X, self.Y, self.B
         else:
             it = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(dev)
             Xb, Yb, b = self.X.index_select(0, it).contiguous(), self.Y.index_select(0, it).contiguous(), len(idx)
-        out, info = self._out[:b], self._info[:b]
+            if nr is not None:
+                nr = nr.index_select(0, it).contiguous()
+        if slot == 0:
+            out, info = self._out[:b], self._info[:b]
+        else:
+            if self._out2 is None:
+                self._out2, self._info2 = torch.empty_like(self._out), torch.zeros_like(self._info)
+            out, info = self._out2[:b], self._info2[:b]
         eng.batched_lml_grad(Xb.data_ptr(), Yb.data_ptr(), th.data_ptr(), nz.data_ptr(), b, self.N, self.D,
-                             out.data_ptr(), info.data_ptr(), want_grad)
+                             out.data_ptr(), info.data_ptr(), want_grad, None if nr is None else nr.data_ptr())
+        # (the inputs th, nz, Xb, Yb stay referenced by the caller-visible tensors of this stream-ordered launch;
+        # torch's caching allocator does not reuse them before the kernel has run on the same stream)
         return out, info
 
     def lml_and_grads(self, theta: Optional[np.ndarray] = None, noise: Optional[np.ndarray] = None,
-                      idx: Optional[np.ndarray] = None, want_grad: bool = True):
-        """(lml [b], dlml/dtheta [b,P] constrained, dlml/dnoise [b], info [b]) as numpy arrays."""
-        theta = self.theta if theta is None else theta
-        noise = self.noise if noise is None else noise
-        if idx is not None and theta.shape[0] == self.B:
-            theta, noise = theta[idx], noise[idx]
+                      idx: Optional[np.ndarray] = None, want_grad: bool = True, subset_params: bool = False):
+        """(lml [b], dlml/dtheta [b,P] constrained, dlml/dnoise [b], info [b]) as numpy arrays.
+
+        ``idx`` selects the GPs (rows of X, Y).  ``theta`` / ``noise`` are FULL-batch arrays ([B, P], [B]) that
+        are indexed with ``idx`` here, unless ``subset_params=True``: then they already hold one row per entry
+        of ``idx``, in that order (the lock-step driver's case).  Nothing is inferred from shapes."""
+        theta = self.theta if theta is None else np.asarray(theta)
+        noise = self.noise if noise is None else np.asarray(noise)
+        if idx is not None:
+            if subset_params:
+                if theta.shape[0] != len(idx) or noise.shape[0] != len(idx):
+                    raise ValueError("subset_params=True: theta and noise need one row per entry of idx")
+            else:
+                if theta.shape[0] != self.B or noise.shape[0] != self.B:
+                    raise ValueError("theta and noise must be full-batch arrays ([B, P], [B]); pass subset_params=True for per-idx rows")
+                theta, noise = theta[idx], noise[idx]
         out, info = self._launch(theta, noise, idx, want_grad)
         o = out.cpu().numpy()
         return o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), info.cpu().numpy()
@@ -289,26 +391,61 @@ class BatchedGPR:
         noise = self._noise_tf.forward(U[:, nt]) if self.train_noise else self.noise[idx].copy()
         return theta, noise
 
-    def loss_and_grads_unconstrained(self, U: np.ndarray, idx: np.ndarray):
-        """training_loss (= -LML) and its gradient w.r.t. the packed unconstrained variables."""
-        theta, noise = self._unpack(U, idx)
-        lml, gth, gnz, info = self.lml_and_grads(theta, noise, idx)
+    # A trial point where K + s2 I is not positive definite: GPflow / TF raise out of ``minimize`` there
+    # (InvalidArgumentError) and the whole fit is lost.  In a batch one bad GP must not take
+    # the others down, so its objective is reported as this large FINITE value with a zero gradient: SciPy's
+    # line search (dcsrch) backs off from it like from any too-long step, where +inf would turn its
+    # interpolation into NaN.  The GP is recorded in ``self.non_pd_evaluations`` and its iterates may differ
+    # from what a run that never hits such a point would give -- for those GPs the "iterates are SciPy's own"
+    # guarantee is about the SciPy state machine, not about GPflow (which would have raised).
+    NON_PD_PENALTY = 1e100
+
+    def _finish_unconstrained(self, U, idx, lml, gth, gnz, info):
         nt = int(self.trainable_mask.sum())
         g = -gth[:, self.trainable_mask] * self._theta_tf.forward_grad(U[:, :nt])
         if self.train_noise:
             g = np.concatenate([g, (-gnz * self._noise_tf.forward_grad(U[:, nt]))[:, None]], axis=1)
         f = -lml
         bad = info != 0
-        if np.any(bad):  # non-PD at a trial point: GPflow would raise; here the line search backs off
-            f = np.where(bad, np.inf, f)
+        if np.any(bad):
+            f = np.where(bad, self.NON_PD_PENALTY, f)
             g = np.where(bad[:, None], 0.0, g)
+            np.add.at(self.non_pd_evaluations, np.asarray(idx)[bad], 1)
         return f, g
+
+    def loss_and_grads_unconstrained(self, U: np.ndarray, idx: np.ndarray):
+        """training_loss (= -LML) and its gradient w.r.t. the packed unconstrained variables."""
+        theta, noise = self._unpack(U, idx)
+        lml, gth, gnz, info = self.lml_and_grads(theta, noise, idx, subset_params=True)
+        return self._finish_unconstrained(U, idx, lml, gth, gnz, info)
+
+    def loss_and_grads_unconstrained_async(self, U: np.ndarray, idx: np.ndarray):
+        """Start the evaluation (H2D copies and the kernel go onto the stream) and return ``wait() -> (f, g)``;
+        two evaluations may be in flight (alternating result buffers)."""
+        U = np.array(U, dtype=np.float64)
+        idx = np.array(idx, dtype=np.int64)
+        theta, noise = self._unpack(U, idx)
+        slot = self._flip
+        self._flip ^= 1
+        out, info = self._launch(theta, noise, idx, True, slot=slot)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.X.device))
+
+        def wait():
+            ev.synchronize()
+            o = out.cpu().numpy()
+            return self._finish_unconstrained(U, idx, o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), info.cpu().numpy())
+
+        return wait
 
     def fit(self, maxiter: int = 15000, **lbfgs_kwargs) -> List[scipy.optimize.OptimizeResult]:
         """Scipy().minimize(model.training_loss, model.trainable_variables) for every GP, lock step.
         ``workers=k`` (k > 1) advances the SciPy state machines in k worker processes (same iterates)."""
         U0 = self._pack()
-        res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter, **lbfgs_kwargs)
+        self.non_pd_evaluations = np.zeros(self.B, dtype=np.int64)
+        pipelined = lbfgs_kwargs.pop("pipelined", self.B >= 64)
+        res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter,
+                              fun_batch_async=self.loss_and_grads_unconstrained_async if pipelined else None, **lbfgs_kwargs)
         U = np.stack([r.x for r in res])
         self.theta, self.noise = self._unpack(U, np.arange(self.B))
         return res
@@ -328,5 +465,6 @@ class BatchedGPR:
         mean = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
         var = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
         eng.batched_predict_f(self.X.data_ptr(), self.Y.data_ptr(), th.data_ptr(), nz.data_ptr(), self.B, self.N, self.D,
-                              Xs.data_ptr(), Ns, mean.data_ptr(), var.data_ptr(), self._info.data_ptr())
+                              Xs.data_ptr(), Ns, mean.data_ptr(), var.data_ptr(), self._info.data_ptr(),
+                              None if self._nrows_dev is None else self._nrows_dev.data_ptr())
         return mean, var

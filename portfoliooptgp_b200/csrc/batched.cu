@@ -15,8 +15,8 @@
 namespace gpb {
 
 int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta, const double* d_noise,
-                   int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int64_t Ns,
-                   double* d_mean, double* d_var) {
+                   const int* d_nrows, int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs,
+                   int64_t Ns, double* d_mean, double* d_var) {
     if (!h->has_spec) return set_error(h, -3, "batched: no kernel set (gpb_set_kernel)");
     if (B <= 0) return 0;
     if (N < 1 || N > 128) return set_error(h, -2, "batched: N=%lld outside [1,128] (one GP per CTA in shared memory)", (long long)N);
@@ -28,7 +28,7 @@ int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const d
     for (int g = 0; g < h->spec.n_groups; ++g)
         if (h->spec.groups[g].ard_index >= 0) fast = false;
     const int n = (int)N, ns = (int)Ns;
-    if (!fast) return launch_batched_generic(dp, h, d_X, d_Yc, d_theta, d_noise, B, n, D, mode, d_out, d_info, d_Xs, ns, d_mean, d_var);
+    if (!fast) return launch_batched_generic(dp, h, d_X, d_Yc, d_theta, d_noise, d_nrows, B, n, D, mode, d_out, d_info, d_Xs, ns, d_mean, d_var);
     // expression shape (structure only: a descriptor built with a dummy theta is enough to match it)
     if (h->use_shapes) {
         double ones[GPB_MAX_PARAMS];
@@ -37,8 +37,8 @@ int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const d
         build_dev_kernel_core(h->spec, ones, &probe);
         const int shape = match_shape(probe);
         if (shape != SHAPE_NONE) {
-            const int rc = launch_batched_static(shape, dp, h, d_X, d_Yc, d_theta, d_noise, B, n, D, mode, d_out, d_info, d_Xs, ns,
-                                                 d_mean, d_var);
+            const int rc = launch_batched_static(shape, dp, h, d_X, d_Yc, d_theta, d_noise, d_nrows, B, n, D, mode, d_out, d_info,
+                                                 d_Xs, ns, d_mean, d_var);
             if (rc != -100) return rc;   // -100: no straight-line instantiation for this (shape, DP)
         }
     }

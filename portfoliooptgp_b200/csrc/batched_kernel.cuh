@@ -41,8 +41,8 @@ constexpr size_t batched_smem_bytes() { return (size_t)(BatchedSmem::XS + 128 * 
 template <int DP, bool FAST, class SH = DynShape>
 __global__ void __launch_bounds__(BT, 1)
 batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kbad, const double* __restrict__ X,
-                  const double* __restrict__ Yc, const double* __restrict__ noise,
-                  int N, int D, int mode, double* __restrict__ out, int* __restrict__ info,
+                  const double* __restrict__ Yc, const double* __restrict__ noise, const int* __restrict__ nrows,
+                  int Nmax, int D, int mode, double* __restrict__ out, int* __restrict__ info,
                   const double* __restrict__ Xs_new, int Ns, double* __restrict__ mean_out,
                   double* __restrict__ var_out, long long* __restrict__ prof) {
     using SHE = UnitWeights<SH>;   // element routines: the per-GP descriptor is in global memory
@@ -62,12 +62,15 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
+    // ragged batches (expanding windows, Multi-Input_GPR/main.py:414-423): GP b uses the first nrows[b] of its
+    // Nmax rows; the rest of its tile is identity padding like the round-up to a multiple of 8
+    const int N = nrows ? min(max(nrows[b], 1), Nmax) : Nmax;
     const int np = (N + 7) & ~7;
     // per-GP kernel descriptor, built by build_dev_kernels_kernel; read-only global memory (not shared
     // memory) so that the compiler may keep its loop-invariant fields in registers
     const DevKernel& kp = kps[b];
     const int P = kp.n_params;
-    const double* Xb = X + (size_t)b * N * D;
+    const double* Xb = X + (size_t)b * Nmax * D;
 
     const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && tid == 0;
     if (do_prof) prof[0] = clock64();
@@ -76,7 +79,7 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
         const int r = e / DP, d = e % DP;
         xs[r * XSTR + d] = (r < N && d < D) ? Xb[r * D + d] : 0.0;
     }
-    if (tid < 128) ys[tid] = (tid < N) ? Yc[(size_t)b * N + tid] : 0.0;
+    if (tid < 128) ys[tid] = (tid < N) ? Yc[(size_t)b * Nmax + tid] : 0.0;
     __syncthreads();
     const double nv = noise[b];
     if (do_prof) prof[1] = clock64();
@@ -275,8 +278,8 @@ static __global__ void build_dev_kernels_kernel(const __grid_constant__ gpb_kern
 
 template <int DP, bool FAST, class SH = DynShape>
 static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
-                             const double* d_noise, int64_t B, int N, int D, int mode, double* d_out, int* d_info,
-                             const double* d_Xs, int Ns, double* d_mean, double* d_var) {
+                             const double* d_noise, const int* d_nrows, int64_t B, int N, int D, int mode, double* d_out,
+                             int* d_info, const double* d_Xs, int Ns, double* d_mean, double* d_var) {
     auto kern = batched_gp_kernel<DP, FAST, SH>;
     constexpr size_t SMEM = batched_smem_bytes<DP>();
     static bool attr_set[GPB_MAX_DEVICES] = {};
@@ -299,7 +302,7 @@ static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Y
     {
         ProfScope prof(h, PROF_BATCHED, h->stream);
         build_dev_kernels_kernel<<<(unsigned)((B + 127) / 128), 128, 0, h->stream>>>(h->spec, d_theta, B, kps, kbad);
-        kern<<<(unsigned)B, BT, SMEM, h->stream>>>(kps, kbad, d_X, d_Yc, d_noise, N, D, mode, d_out, d_info, d_Xs, Ns,
+        kern<<<(unsigned)B, BT, SMEM, h->stream>>>(kps, kbad, d_X, d_Yc, d_noise, d_nrows, N, D, mode, d_out, d_info, d_Xs, Ns,
                                                     d_mean, d_var, want_prof ? d_prof : nullptr);
         h->launches += 1;
     }
@@ -317,8 +320,9 @@ static int launch_batched_dp(gpb_handle* h, const double* d_X, const double* d_Y
 
 // launchers instantiated in other translation units (compile time: one object per kernel family)
 #define GPB_BATCHED_PARAMS gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta, const double* d_noise, \
-    int64_t B, int N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int Ns, double* d_mean, double* d_var
-#define GPB_BATCHED_ARGS h, d_X, d_Yc, d_theta, d_noise, B, N, D, mode, d_out, d_info, d_Xs, Ns, d_mean, d_var
+    const int* d_nrows, int64_t B, int N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int Ns, double* d_mean, \
+    double* d_var
+#define GPB_BATCHED_ARGS h, d_X, d_Yc, d_theta, d_noise, d_nrows, B, N, D, mode, d_out, d_info, d_Xs, Ns, d_mean, d_var
 int launch_batched_generic(int dp, GPB_BATCHED_PARAMS);          // batched_generic.cu: interpreter, any expression (ARD, > 4 leaves)
 int launch_batched_static(int shape, int dp, GPB_BATCHED_PARAMS); // batched_shapes.cu: straight-line shapes; -100 = no such instantiation
 

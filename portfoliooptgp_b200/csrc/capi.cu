@@ -410,8 +410,28 @@ int gpb_batched_lml_grad(gpb_handle* h, const double* d_X, const double* d_Yc, c
                          int want_grad) {
     GPB_ENTER(h);
     if (!d_X || !d_Yc || !d_theta || !d_noise || !d_out || !d_info) return set_error(h, -2, "batched_lml_grad: null pointer");
-    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, B, N, D, want_grad ? 1 : 0, d_out, d_info, nullptr, 0, nullptr,
-                          nullptr);
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, nullptr, B, N, D, want_grad ? 1 : 0, d_out, d_info, nullptr, 0,
+                          nullptr, nullptr);
+}
+
+int gpb_batched_lml_grad_ragged(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                                const double* d_noise, const int32_t* d_nrows, int64_t B, int64_t Nmax, int D, double* d_out,
+                                int32_t* d_info, int want_grad) {
+    GPB_ENTER(h);
+    if (!d_X || !d_Yc || !d_theta || !d_noise || !d_nrows || !d_out || !d_info)
+        return set_error(h, -2, "batched_lml_grad_ragged: null pointer");
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, d_nrows, B, Nmax, D, want_grad ? 1 : 0, d_out, d_info, nullptr, 0,
+                          nullptr, nullptr);
+}
+
+int gpb_batched_predict_f_ragged(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
+                                 const double* d_noise, const int32_t* d_nrows, int64_t B, int64_t Nmax, int D,
+                                 const double* d_Xs, int64_t Ns, double* d_mean, double* d_var, int32_t* d_info) {
+    GPB_ENTER(h);
+    if (!d_X || !d_Yc || !d_theta || !d_noise || !d_nrows || !d_Xs || !d_mean || !d_var || !d_info)
+        return set_error(h, -2, "batched_predict_f_ragged: null pointer");
+    if (Ns <= 0) return 0;
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, d_nrows, B, Nmax, D, 2, nullptr, d_info, d_Xs, Ns, d_mean, d_var);
 }
 
 int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta,
@@ -421,7 +441,7 @@ int gpb_batched_predict_f(gpb_handle* h, const double* d_X, const double* d_Yc, 
     if (!d_X || !d_Yc || !d_theta || !d_noise || !d_Xs || !d_mean || !d_var || !d_info)
         return set_error(h, -2, "batched_predict_f: null pointer");
     if (Ns <= 0) return 0;
-    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, B, N, D, 2, nullptr, d_info, d_Xs, Ns, d_mean, d_var);
+    return launch_batched(h, d_X, d_Yc, d_theta, d_noise, nullptr, B, N, D, 2, nullptr, d_info, d_Xs, Ns, d_mean, d_var);
 }
 
 }  // extern "C"

@@ -222,9 +222,10 @@ int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double
                   double* d_var, int64_t reuse_serial = -1);
 
 // ---- batched.cu: one GP per CTA.  mode 0 = LML, 1 = LML + gradient, 2 = predict_f
+// d_nrows (optional, [B] ints): GP b uses the first d_nrows[b] of its N rows (ragged batches)
 int launch_batched(gpb_handle* h, const double* d_X, const double* d_Yc, const double* d_theta, const double* d_noise,
-                   int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs, int64_t Ns,
-                   double* d_mean, double* d_var);
+                   const int* d_nrows, int64_t B, int64_t N, int D, int mode, double* d_out, int* d_info, const double* d_Xs,
+                   int64_t Ns, double* d_mean, double* d_var);
 
 // ---- svgp.cu
 int svgp_data_term(gpb_handle* h, const double* theta, double s2, const double* d_Z, int64_t M, int D,

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import ops
@@ -149,3 +150,25 @@ def rolling_windows(features, y=None, window: int = 128, stride: int = 1, device
         _engine_for(f).prep_windows(f.data_ptr(), None if yt is None else yt.data_ptr(), S, T, D, window, stride,
                                     X.data_ptr(), None if Y is None else Y.data_ptr())
     return (X, Y) if y is not None else X
+
+
+def expanding_windows(features, y, first: int, count: int, device=None):
+    """The reference's rolling re-fit as ONE ragged batch (Multi-Input_GPR/main.py:414-423): test day k
+    (k = 0 .. count-1) fits a fresh GPR on ``X_full[:first + k]``.  Returns ``(X [count, Nmax, D],
+    Y [count, Nmax, 1], nrows [count], Xnew [count, 1, D])`` with Nmax = first + count - 1: every GP sees the
+    same leading rows, ``nrows[k] = first + k`` says how many it uses, and ``Xnew[k]`` is the next row -- the
+    one whose prediction the reference keeps (``predict_f(X_full[:i+1])[-1]``, main.py:434,454).  Feed
+    ``BatchedGPR(X, Y, kernel, nrows=nrows)`` and ``predict_f(Xnew)``.  ``features`` needs first + count rows."""
+    f = ops.to_device(features, device)
+    if f.ndim != 2:
+        raise ValueError("features must be [T, D]")
+    yt = ops.to_device(y, f.device.index).reshape(-1)
+    T, D = f.shape
+    if first < 1 or count < 1 or first + count > T or yt.shape[0] != T:
+        raise ValueError("expanding_windows needs 1 <= first, 1 <= count and first + count <= T rows of features and y")
+    nmax = first + count - 1
+    X = f[:nmax].unsqueeze(0).expand(count, nmax, D).contiguous()
+    Y = yt[:nmax].reshape(1, nmax, 1).expand(count, nmax, 1).contiguous()
+    nrows = np.arange(first, first + count, dtype=np.int32)
+    Xnew = torch.stack([f[first + k] for k in range(count)])[:, None, :].contiguous()
+    return X, Y, nrows, Xnew

@@ -111,3 +111,44 @@ def test_lockstep_workers_reproduce_the_in_process_iterates():
     for a, b in zip(r0, r1):
         assert np.array_equal(a.x, b.x) and a.fun == b.fun and np.array_equal(a.jac, b.jac)
         assert (a.nit, a.nfev, a.status, a.message) == (b.nit, b.nfev, b.status, b.message)
+
+
+def test_pipelined_halves_give_the_same_iterates():
+    """Two half-batches in flight (device evaluates one while the host advances the other): every problem still
+    sees its own (x, f, g) sequence, so the results equal the single-batch lock-step run bit for bit."""
+    rng = np.random.default_rng(3)
+    B, n = 11, 4
+    coeffs = rng.uniform(1.0, 100.0, size=B)
+    X0 = rng.uniform(-1.5, 1.5, size=(B, n))
+    funs = [_rosen_family(a) for a in coeffs]
+    in_flight = []
+
+    def fun_batch(X, idx):
+        return (np.array([funs[b][0](x) for x, b in zip(X, idx)]), np.stack([funs[b][1](x) for x, b in zip(X, idx)]))
+
+    def fun_batch_async(X, idx):
+        X, idx = X.copy(), idx.copy()
+        in_flight.append(1)
+
+        def wait():
+            in_flight.pop()
+            return fun_batch(X, idx)
+        assert len(in_flight) <= 2
+        return wait
+
+    a = lockstep_lbfgsb(fun_batch, X0, maxiter=60)
+    b = lockstep_lbfgsb(fun_batch, X0, maxiter=60, fun_batch_async=fun_batch_async)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra.x, rb.x) and ra.fun == rb.fun and ra.nit == rb.nit and ra.nfev == rb.nfev and ra.status == rb.status
+
+
+def test_old_scipy_gets_a_clear_error(monkeypatch):
+    """the driver uses SciPy's private C setulb (>= 1.15); anything else must fail with a message,
+    not with a TypeError from inside the first fit."""
+    import pytest
+    from portfoliooptgp_b200 import batched
+    monkeypatch.setattr(batched, "_SCIPY_CHECKED", None)
+    monkeypatch.setattr(batched.scipy, "__version__", "1.13.0")
+    with pytest.raises(RuntimeError, match="SciPy >= 1.15"):
+        lockstep_lbfgsb(lambda X, idx: (np.zeros(len(idx)), np.zeros_like(X)), np.zeros((2, 2)))
+    monkeypatch.setattr(batched, "_SCIPY_CHECKED", None)

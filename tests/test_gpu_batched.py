@@ -88,3 +88,58 @@ def test_batched_fit_equals_per_gp_scipy_fit(gp):
         assert r.nit == res[b].nit
         assert abs(r.fun - res[b].fun) <= 1e-6 * max(1.0, abs(r.fun))
         assert np.max(np.abs(r.x - res[b].x)) < 1e-5
+
+
+def test_expanding_windows_as_one_ragged_batch_match_the_reference_loop(gp):
+    """Multi-Input_GPR/main.py:414-456: test day k fits a fresh GPR on X_full[:i], i = 63 + k, and keeps
+    predict_f(X_full[:i+1])[-1].  As ONE ragged batch (per-GP row counts): every GP's LML, gradient and
+    one-step-ahead prediction equal the oracle's on exactly the rows the reference gives it."""
+    from oracle import gpflow_oracle as O
+    from portfoliooptgp_b200.data_prep import expanding_windows
+    D, first, count = 7, 63, 5
+    Xf, Yf = make_multi_input(17, first + count, D)
+    K = gp.kernels
+    k = K.Exponential(variance=1.1, lengthscales=1.6, active_dims=slice(0, D - 1)) * K.Exponential(variance=0.8, lengthscales=0.9, active_dims=slice(D - 1, D))
+    X, Y, nrows, Xnew = expanding_windows(Xf, Yf, first, count)
+    assert list(nrows) == [63, 64, 65, 66, 67] and tuple(X.shape) == (5, 67, 7)
+    m = gp.BatchedGPR(X, Y, k, noise_variance=1e-3, nrows=nrows)           # noise_variance=1e-3: main.py:422
+    lml, gth, gnz, info = m.lml_and_grads()
+    mean, var = m.predict_f(Xnew)
+    ko = to_oracle(k)
+    O.set_distance_form("direct")
+    try:
+        for b, i in enumerate(nrows):
+            l0, g0, n0 = O.gpr_lml_and_grad(ko, Xf[:i], Yf[:i], 1e-3)
+            m0, v0 = O.gpr_predict_f(ko, Xf[:i], Yf[:i], 1e-3, Xf[i:i + 1])
+            assert info[b] == 0
+            assert abs(lml[b] - l0) <= 1e-9 * abs(l0)
+            assert np.max(np.abs(gth[b] - g0)) <= 1e-7 * max(1.0, np.max(np.abs(g0))) and abs(gnz[b] - n0) <= 1e-7 * max(1.0, abs(n0))
+            assert abs(float(mean[b, 0]) - m0[0, 0]) <= 1e-9 * max(1.0, abs(m0[0, 0]))
+            assert abs(float(var[b, 0]) - v0[0, 0]) <= 1e-9 * max(1.0, abs(v0[0, 0]))
+    finally:
+        O.set_distance_form("gram")
+    # a subset evaluation keeps each GP's own row count
+    l_sub, _, _, _ = m.lml_and_grads(idx=np.array([3, 1]))
+    assert l_sub[0] == lml[3] and l_sub[1] == lml[1]
+
+
+def test_pipelined_fit_equals_plain_lockstep_fit_and_flags_are_explicit(gp):
+    """fit(): two half-batches in flight by default; same iterates as the plain lock-step run.  And the
+    full-batch / per-idx meaning of theta in lml_and_grads is a flag, not a shape guess."""
+    B, N, D = 96, 64, 3
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((B, N, D))
+    Y = np.sin(X[:, :, 0]) + 0.1 * rng.standard_normal((B, N))
+    k = gp.kernels.SquaredExponential(lengthscales=1.2)
+    a = gp.BatchedGPR(X, Y, k, noise_variance=0.1)
+    b = gp.BatchedGPR(X, Y, k, noise_variance=0.1)
+    ra = a.fit(maxiter=30, pipelined=False)
+    rb = b.fit(maxiter=30)
+    assert all(np.array_equal(x.x, y.x) and x.nit == y.nit and x.fun == y.fun for x, y in zip(ra, rb))
+    assert int(b.non_pd_evaluations.sum()) == 0
+    idx = np.array([5, 2, 9])
+    full = b.lml_and_grads(b.theta, b.noise, idx)[0]
+    sub = b.lml_and_grads(b.theta[idx], b.noise[idx], idx, subset_params=True)[0]
+    assert np.array_equal(full, sub)
+    with pytest.raises(ValueError):
+        b.lml_and_grads(b.theta[idx], b.noise[idx], idx)
