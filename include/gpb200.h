@@ -111,7 +111,9 @@ int64_t gpb_launch_count(gpb_handle* h);
  * csrc/cholesky.cu) for N >= 3072 (default 0 = the single-partition recursion: on B200 the pipeline's
  * rank-1024 products run at 0.90 of the recursion's large-K products and the 8 reserved SMs cost 5 %,
  * which outweighs the hidden latency -- 22.8 vs 21.3 ms at N = 8192, profiles/r02_pipeline_ab.txt;
- * silently off when the driver cannot create the partitions). */
+ * silently off when the driver cannot create the partitions).  option 5: the look-ahead chain over the
+ * 128-row leaves of every <= 1024-row diagonal block at the bottom of the blocked factorisation
+ * (default 1; 0 = the plain 2 x 2 recursion down to the leaves). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 /* Diagnostics: which straight-line shape (csrc/shapes.cuh, 1-based id) the current expression matches;
  * 0 = none, the run-time interpreter evaluates it (also when option 2 is off).  < 0: error. */

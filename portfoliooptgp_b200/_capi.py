@@ -186,6 +186,7 @@ class Engine:
     OPTION_PDL = 1
     OPTION_STATIC_SHAPES = 2
     OPTION_REFINE_OBJECTIVE = 3   # 0 never, 1 automatic (ill-conditioned K only), 2 always
+    OPTION_CHAIN = 5              # look-ahead chain at the bottom of the blocked factorisation (default on)
     OPTION_PIPELINE = 4           # two-partition pipelined factorisation for N >= 3072 (default off: measured slower)
 
     def set_option(self, option: int, value: int):

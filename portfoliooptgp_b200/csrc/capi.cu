@@ -189,6 +189,7 @@ int gpb_destroy(gpb_handle* h) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     partitions_destroy(h);
+    for (cudaEvent_t e : h->chain_events) cudaEventDestroy(e);
     for (int i = 0; i < gpb_handle::N_BUF; ++i)
         if (h->buf[i]) cudaFree(h->buf[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -230,6 +231,7 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
         case 1: h->use_pdl = (value != 0); return 0;
         case 2: h->use_shapes = (value != 0); return 0;
         case 4: h->use_pipeline = (value != 0); return 0;
+        case 5: h->use_chain = (value != 0); return 0;
         case 3:
             if (value < 0 || value > 2) return set_error(h, -2, "option 3 (objective refinement) takes 0, 1 or 2");
             h->refine_mode = value;

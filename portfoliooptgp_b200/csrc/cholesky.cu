@@ -112,9 +112,118 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
 // (needs U scratch of n2 x n1 doubles).
 // info_base: added to the reported pivot index (the block may sit at row info_base of a larger matrix whose
 // diagonal blocks are factorised one by one, factor_L below).
+// ---- the bottom of the recursion as a look-ahead chain -----------------------------------------------------
+// A diagonal block of n <= chain_max() rows (1024): right-looking over its 128-row leaves k = 0 .. nb-1,
+//   critical stream:  D_k (leaf: L_kk, W_kk)  ->  P_k  T[k+1:, k] = A[k+1:, k] W_kk^T
+//                                             ->  Sa_k A[k+1:, k+1] -= T[k+1:, k] T[k+1, k]^T   (next leaf's column)
+//   side stream:      Sb_k A[k+2:, k+2:] -= T[k+2:, k] T[k+2:, k]^T ;  R_k  W[k, :k] = -W_kk (T[k, :k] W[:k, :k])
+// The 2 x 2 recursion puts EVERY product of a node on the path to the next leaf (its W21 = -W22 U closes the
+// node before the parent may use W11): 82 us per leaf at n = 1024 for a 35 us leaf.  Here the next leaf waits
+// for one panel product and one 128-column update only; the rest of the trailing update and the rows of the
+// inverse run beside the next leaf.  Same flop, same storage (T lives in W's off-diagonal part until R_k
+// replaces it by the inverse; V = T W goes through A's dead off-diagonal part, or through scratch when keepL
+// keeps L there).  gpb_set_option(h, 5, 0) restores the plain recursion.
+static cudaEvent_t chain_event(gpb_handle* h, size_t i) {
+    while (h->chain_events.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        h->chain_events.push_back(e);
+    }
+    return h->chain_events[i];
+}
+
+static int chain_max() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPB_CHAIN_MAX");
+        v = e ? atoi(e) : 1024;
+        if (v < 2 * NB) v = 0;
+    }
+    return v;
+}
+
+static int factor_inv_chain(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
+                            int* info, bool keepL, double* scratchU, int depth, int info_base) {
+    const int nb = (n + NB - 1) / NB;
+    const bool fork = h->fork_streams && depth < gpb_handle::MAX_DEPTH && h->side[depth];
+    cudaStream_t SA = h->stream, SB = fork ? h->side[depth] : h->stream;
+    auto off = [&](int k) { return (int64_t)o + (int64_t)k * NB; };
+    auto size = [&](int k) { return (k == nb - 1) ? (n - k * NB) : NB; };
+    // events: 2k = P_k done (critical stream), 2k + 1 = Sb_k done (side stream); shared pool, chains never nest
+    auto evP = [&](int k) { return chain_event(h, 2 * (size_t)k); };
+    auto evSb = [&](int k) { return chain_event(h, 2 * (size_t)k + 1); };
+    if (fork && (!evP(nb) || !evSb(nb))) return set_error(h, -1, "chain: event creation failed");
+#define GPB_CU(call, what)                                  \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return check_cuda(h, e_, what); \
+    } while (0)
+    int rc;
+    GemmArgs g;
+    const int64_t end = (int64_t)o + n;
+    for (int k = 0; k < nb; ++k) {
+        const int64_t rk = off(k);
+        const int nk = size(k);
+        double* Wkk = W + rk * ldw + rk;
+        if ((rc = leaf(h, A, lda, W, ldw, nk, (int)rk, logdiag, info, keepL, info_base))) return rc;
+        if (k + 1 < nb) {
+            const int64_t r1 = off(k + 1), m1 = end - r1;
+            const int n1 = size(k + 1);
+            g = GemmArgs();   // P_k
+            g.transa = 0; g.transb = 1; g.M = m1; g.N = nk; g.K = nk;
+            g.A = A + r1 * lda + rk; g.lda = lda; g.B = Wkk; g.ldb = ldw; g.C = W + r1 * ldw + rk; g.ldc = ldw; g.b_upper = 1;
+            if ((rc = launch_gemm(h, g, SA))) return rc;
+            if (fork) GPB_CU(cudaEventRecord(evP(k), SA), "chain record P");
+            if (fork && k > 0) GPB_CU(cudaStreamWaitEvent(SA, evSb(k - 1), 0), "chain wait Sb");
+            g = GemmArgs();   // Sa_k
+            g.transa = 0; g.transb = 1; g.M = m1; g.N = n1; g.K = nk; g.alpha = -1.0; g.beta = 1.0;
+            g.A = W + r1 * ldw + rk; g.lda = ldw; g.B = g.A; g.ldb = ldw; g.C = A + r1 * lda + r1; g.ldc = lda;
+            if ((rc = launch_gemm(h, g, SA))) return rc;
+        }
+        if (fork && (k + 1 < nb || k > 0)) {
+            if (k + 1 < nb) GPB_CU(cudaStreamWaitEvent(SB, evP(k), 0), "chain wait P");
+            else {   // last block: its row of the inverse needs the leaf only
+                GPB_CU(cudaEventRecord(evP(k), SA), "chain record D");
+                GPB_CU(cudaStreamWaitEvent(SB, evP(k), 0), "chain wait D");
+            }
+        }
+        if (k + 2 < nb) {
+            const int64_t r2 = off(k + 2), m2 = end - r2;
+            g = GemmArgs();   // Sb_k
+            g.transa = 0; g.transb = 1; g.M = m2; g.N = m2; g.K = nk; g.alpha = -1.0; g.beta = 1.0;
+            g.A = W + r2 * ldw + rk; g.lda = ldw; g.B = g.A; g.ldb = ldw; g.C = A + r2 * lda + r2; g.ldc = lda; g.tri = 1;
+            if ((rc = launch_gemm(h, g, SB))) return rc;
+        }
+        if (fork && k + 1 < nb) GPB_CU(cudaEventRecord(evSb(k), SB), "chain record Sb");
+        if (k > 0) {
+            const int64_t w = rk - o;   // width of the finished part of the block
+            double* V = keepL ? scratchU : A + rk * lda + o;
+            const int64_t ldv = keepL ? w : lda;
+            g = GemmArgs();   // V = T[k, :k] W[:k, :k]
+            g.transa = 0; g.transb = 0; g.M = nk; g.N = w; g.K = w;
+            g.A = W + rk * ldw + o; g.lda = ldw; g.B = W + (int64_t)o * ldw + o; g.ldb = ldw; g.C = V; g.ldc = ldv; g.b_lower = 1;
+            if ((rc = launch_gemm(h, g, SB))) return rc;
+            if (keepL)   // keep L[k, :k] (= T) under the diagonal of A before the inverse overwrites it in W
+                GPB_CU(cudaMemcpy2DAsync(A + rk * lda + o, lda * sizeof(double), W + rk * ldw + o, ldw * sizeof(double),
+                                         (size_t)w * sizeof(double), (size_t)nk, cudaMemcpyDeviceToDevice, SB), "chain copy L");
+            g = GemmArgs();   // W[k, :k] = -W_kk V
+            g.transa = 0; g.transb = 0; g.M = nk; g.N = w; g.K = nk; g.alpha = -1.0;
+            g.A = Wkk; g.lda = ldw; g.B = V; g.ldb = ldv; g.C = W + rk * ldw + o; g.ldc = ldw; g.a_lower = 1;
+            if ((rc = launch_gemm(h, g, SB))) return rc;
+        }
+    }
+    if (fork && nb > 1) {
+        GPB_CU(cudaEventRecord(evSb(nb), SB), "chain record join");
+        GPB_CU(cudaStreamWaitEvent(SA, evSb(nb), 0), "chain join");
+    }
+#undef GPB_CU
+    return 0;
+}
+
 static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
                           int* info, bool keepL, double* scratchU, int depth, int info_base = 0) {
     if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info, keepL, info_base);
+    if (h->use_chain && n <= chain_max()) return factor_inv_chain(h, A, lda, W, ldw, o, n, logdiag, info, keepL, scratchU, depth, info_base);
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1, o2 = o + n1;
     int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1, info_base);
     if (rc) return rc;
@@ -177,12 +286,22 @@ static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int6
 }
 
 // scratch doubles needed by keepL at size n (sum over the recursion's live U blocks)
+// scratch doubles keepL needs at size n: the recursion's live U blocks, and -- for a block the look-ahead chain
+// may take (the option can change between calls, so both are covered) -- the chain's V block, size(k) x k 128
 static size_t keepL_scratch(int n) {
     if (n <= NB) return 0;
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1;
-    size_t below = keepL_scratch(n1);
-    size_t right = (size_t)n2 * n1 + keepL_scratch(n2);
-    return below > right ? below : right;
+    const size_t below = keepL_scratch(n1);
+    const size_t right = (size_t)n2 * n1 + keepL_scratch(n2);
+    size_t need = below > right ? below : right;
+    if (n <= chain_max()) {
+        const int nb = (n + NB - 1) / NB;
+        for (int k = 1; k < nb; ++k) {
+            const size_t v = (size_t)((k == nb - 1) ? (n - k * NB) : NB) * (size_t)(k * NB);
+            if (v > need) need = v;
+        }
+    }
+    return need;
 }
 
 int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int64_t N, double* logdiag, int* d_info,
@@ -567,23 +686,26 @@ int solve_LT_vec(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd,
     return check_cuda(h, cudaGetLastError(), "solve_LT_vec launches");
 }
 
-// B [N, m] (ldb) <- destroyed; Out [N, m] (ldo) = L^-1 B by block forward substitution (left-looking):
-// B_k -= L_k,<k Out_<k ; Out_k = Wd_k B_k.  N^2 m flop on the DMMA GEMM.
+// B [N, m] (ldb) <- destroyed; Out [N, m] (ldo) = L^-1 B by block forward substitution, right-looking:
+// Out_k = Wd_k B_k ; B_>k -= L_>k,k Out_k.  N^2 m flop on the DMMA GEMM.  (Right-looking keeps M large: the
+// left-looking form updates one 1024-row block per product, 256 tiles on 296 CTA slots -- 27.9 TFLOP/s at
+// N = 65536, m = 2048; this form runs the rank-1024 updates over all remaining rows.)
 int solve_L_mat(gpb_handle* h, const double* Lw, int64_t ldl, const double* Wd, int64_t N, double* B, int64_t ldb, int64_t m,
                 double* Out, int64_t ldo) {
     int rc;
     for (int64_t o = 0; o < N; o += NBD) {
         const int64_t nk = (N - o < NBD) ? (N - o) : NBD;
         GemmArgs g;
-        if (o > 0) {
-            g.transa = 0; g.transb = 0; g.M = nk; g.N = m; g.K = o; g.alpha = -1.0; g.beta = 1.0;
-            g.A = Lw + o * ldl; g.lda = ldl; g.B = Out; g.ldb = ldo; g.C = B + o * ldb; g.ldc = ldb;
-            if ((rc = launch_gemm(h, g, h->stream))) return rc;
-        }
-        g = GemmArgs();
         g.transa = 0; g.transb = 0; g.M = nk; g.N = m; g.K = nk;
         g.A = Wd + o * NBD; g.lda = NBD; g.B = B + o * ldb; g.ldb = ldb; g.C = Out + o * ldo; g.ldc = ldo; g.a_lower = 1;
         if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        const int64_t below = N - (o + nk);
+        if (below > 0) {
+            g = GemmArgs();
+            g.transa = 0; g.transb = 0; g.M = below; g.N = m; g.K = nk; g.alpha = -1.0; g.beta = 1.0;
+            g.A = Lw + (o + nk) * ldl + o; g.lda = ldl; g.B = Out + o * ldo; g.ldb = ldo; g.C = B + (o + nk) * ldb; g.ldc = ldb;
+            if ((rc = launch_gemm(h, g, h->stream))) return rc;
+        }
     }
     return 0;
 }

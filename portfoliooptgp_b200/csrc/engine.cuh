@@ -39,12 +39,14 @@ struct gpb_handle {
     // SM partitions (green contexts, partition.cu) for the pipelined factorisation: streams of the bulk
     // partition and of the small critical-chain partition; gpb_set_option(h, 4, x) switches the pipeline
     bool part_ok = false;
+    bool use_chain = true;      // gpb_set_option(h, 5, x): look-ahead chain over the 128-row leaves of a <= 1024-row diagonal block
     bool use_pipeline = false;  // measured slower than the recursion (profiles/r02_pipeline_ab.txt): opt-in
     cudaStream_t part_bulk = nullptr, part_crit = nullptr;
     cudaStream_t part_crit_side[MAX_DEPTH] = {};
     void* part_ctx[2] = {nullptr, nullptr};
     int part_crit_sms = 0, part_bulk_sms = 0;
     std::vector<cudaEvent_t> part_events;
+    std::vector<cudaEvent_t> chain_events;   // look-ahead chain at the bottom of the factorisation (cholesky.cu)
 
     bool has_spec = false;
     gpb_kernel_spec spec;
