@@ -121,11 +121,14 @@ int gpb_kernel_shape(gpb_handle* h);
 
 /* Optional kernel timing with CUDA events recorded on the handle's stream around each engine
  * launch, by category (0 DMMA GEMM, 1 assembly, 2 Cholesky leaf, 3 fused gradient reduction,
- * 4 vector kernels, 5 batched, 6 SVGP).  gpb_profile_read synchronises, returns the summed
- * milliseconds and launch counts per category (arrays of 8) and resets the log.  bench.py's
- * roofline numbers come from here; leave it off when timing end to end. */
+ * 4 vector kernels, 5 batched, 6 SVGP, 7 DMMA GEMM in its small-tile latency-bound configurations;
+ * category 0 holds the large-tile launches only).  gpb_profile_read synchronises, returns the summed
+ * milliseconds and launch counts per category (arrays of 8) and resets the log;
+ * gpb_profile_read_flops returns (and resets) the flop those GEMM launches executed, by category.
+ * bench.py's roofline numbers come from here; leave it off when timing end to end. */
 int gpb_profile_enable(gpb_handle* h, int on);
 int gpb_profile_read(gpb_handle* h, double* h_ms, int64_t* h_counts);
+int gpb_profile_read_flops(gpb_handle* h, double* h_flops);
 
 /* ---- kernel expression ---------------------------------------------------------------------- */
 /* Replaces the kernel object handed to gpflow.models.GPR(kernel=...) (GPR/model_trainer.py:15). */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "gpb_set_option": (_INT, [_P, _INT, _INT]),
     "gpb_profile_enable": (_INT, [_P, _INT]),
     "gpb_profile_read": (_INT, [_P, _DP, C.POINTER(C.c_int64)]),
+    "gpb_profile_read_flops": (_INT, [_P, _DP]),
     "gpb_set_kernel": (_INT, [_P, C.POINTER(GpbKernelSpec)]),
     "gpb_assemble": (_INT, [_P, _DP, _P, _I64, _P, _I64, _INT, _P, _I64, _INT, _D]),
     "gpb_kdiag": (_INT, [_P, _DP, _P, _I64, _INT, _P]),
@@ -180,7 +181,7 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.gpb_launch_count(self._h))
 
-    PROF_CATEGORIES = ("gemm", "assemble", "leaf", "grad_reduce", "vector", "batched", "svgp", "other")
+    PROF_CATEGORIES = ("gemm", "assemble", "leaf", "grad_reduce", "vector", "batched", "svgp", "gemm_small")
 
     OPTION_FORK_STREAMS = 0
     OPTION_PDL = 1
@@ -201,6 +202,11 @@ class Engine:
         self._check(self._lib.gpb_profile_read(self._h, _as_dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))),
                     "gpb_profile_read")
         return ({c: float(m) for c, m in zip(self.PROF_CATEGORIES, ms)}, {c: int(n) for c, n in zip(self.PROF_CATEGORIES, cnt)})
+
+    def profile_flops(self):
+        fl = np.zeros(8, dtype=np.float64)
+        self._check(self._lib.gpb_profile_read_flops(self._h, _as_dp(fl)), "gpb_profile_read_flops")
+        return {c: float(f) for c, f in zip(self.PROF_CATEGORIES, fl)}
 
     def set_kernel(self, spec: GpbKernelSpec, token=None):
         if token is not None and token == self._spec_token:

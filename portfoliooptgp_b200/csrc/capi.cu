@@ -245,6 +245,16 @@ int gpb_profile_enable(gpb_handle* h, int on) {
     h->profile = (on != 0);
     h->prof_recs.clear();
     h->prof_used = 0;
+    for (int c = 0; c < PROF_NCAT; ++c) h->prof_flops[c] = 0.0;
+    return 0;
+}
+
+int gpb_profile_read_flops(gpb_handle* h, double* h_flops) {
+    if (!h || !h_flops) return -1;
+    for (int c = 0; c < PROF_NCAT; ++c) {
+        h_flops[c] = h->prof_flops[c];
+        h->prof_flops[c] = 0.0;
+    }
     return 0;
 }
 

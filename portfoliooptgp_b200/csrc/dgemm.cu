@@ -240,7 +240,16 @@ static int launch_cfg(gpb_handle* h, const GemmParams& p0, cudaStream_t stream) 
     p.tiles_m = tm;
     int64_t grid = p.tri ? (int64_t)(BM / BN) * tm * (tm + 1) / 2 : (int64_t)tm * tn;
     if (grid <= 0) return 0;
-    ProfScope prof(h, PROF_GEMM, stream);
+    const int cat = (BM >= 128) ? PROF_GEMM : PROF_GEMM_SMALL;
+    if (h->profile) {
+        // flop as executed at tile granularity, to first order: triangular output and triangular operands halve it
+        // (lower-triangular output: 1/2; a triangular operand: 1/2; both, as in K^-1 = W^T W: 1/6)
+        double f = 2.0 * (double)p.M * (double)p.N * (double)p.K;
+        const bool tri_op = p.a_lower || p.a_upper || p.b_lower || p.b_upper;
+        f *= (p.tri && tri_op) ? (1.0 / 6.0) : ((p.tri || tri_op) ? 0.5 : 1.0);
+        h->prof_flops[cat] += f;
+    }
+    ProfScope prof(h, cat, stream);
     {
         cudaError_t le = h->use_pdl ? launch_pdl(kern, dim3((unsigned)grid), dim3(NT), SMEM, stream, p)
                                     : (kern<<<(unsigned)grid, NT, SMEM, stream>>>(p), cudaSuccess);

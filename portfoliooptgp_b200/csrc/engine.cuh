@@ -70,6 +70,7 @@ struct gpb_handle {
     struct ProfRec { int cat; int e0, e1; };
     std::vector<ProfRec> prof_recs;
     size_t prof_used = 0;
+    double prof_flops[8] = {};   // algorithmic flop of the profiled launches by category (GEMM categories only)
 };
 
 namespace gpb {
@@ -99,7 +100,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7, BUF_WD = 8 };
 constexpr int GPB_NBD = 1024;   // factor-only path: diagonal blocks of this size carry explicit inverses (cholesky.cu)
 
-enum ProfCat { PROF_GEMM = 0, PROF_ASSEMBLE = 1, PROF_LEAF = 2, PROF_GRAD = 3, PROF_VEC = 4, PROF_BATCHED = 5, PROF_SVGP = 6, PROF_NCAT = 8 };
+// PROF_GEMM: dgemm_kernel launches with the large (128 x 64) tiles -- the throughput-bound products;
+// PROF_GEMM_SMALL: its 64 x 64 / 32 x 32 configurations -- the latency-bound bottom of the factorisation
+enum ProfCat { PROF_GEMM = 0, PROF_ASSEMBLE = 1, PROF_LEAF = 2, PROF_GRAD = 3, PROF_VEC = 4, PROF_BATCHED = 5, PROF_SVGP = 6, PROF_GEMM_SMALL = 7, PROF_NCAT = 8 };
 // RAII timer: records an event pair around the launches issued in its scope when h->profile is on.
 struct ProfScope {
     gpb_handle* h; int idx; cudaStream_t st;
