@@ -428,6 +428,14 @@ def run_gpu(args):
             "gpu_launches": int(launches), "roofline": roofline, "assembly_roofline": assembly,
             "kernel_ms_per_step": breakdown, "cpu_baseline": cpu, "lml": lml}
     line.update(extras)
+    # the headline workload (one exact GP) does not shard: at N > 1 `value` counts replicas.  The curves of the
+    # configurations that DO shard (BASELINE metric "batched GPs/s at 1-8 GPU") at this N:
+    line["sharded_at_this_n"] = {
+        "c3_gp_evals_per_s": (extras.get("c3_batched") or {}).get("gp_evals_per_s"),
+        "c3_full_fits_per_s": (extras.get("c3_batched") or {}).get("full_fits_per_s"),
+        "c5_rows_per_s": (extras.get("c5_svgp") or {}).get("rows_per_s"),
+        "note": "C3: 5120 independent GPs block-partitioned over the ranks, no data-path collective, one final gather; "
+                "C5: data-parallel minibatches, one NCCL all-reduce per step"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -115,9 +115,19 @@ def load_library() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise EngineError(
-            f"{LIB_PATH} is missing: build it with `python -m portfoliooptgp_b200.build` "
-            "(nvcc, sm_100a).  There is no CPU fallback on this path.")
+        # a fresh clone has no built library (it is git-ignored): build it in-tree once, if nvcc is here
+        # (GPB_NO_AUTOBUILD=1 switches this off); there is no CPU fallback on this path either way
+        err = None
+        if os.environ.get("GPB_NO_AUTOBUILD", "0") in ("", "0"):
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # nvcc missing or a compile error: report it below
+                err = e
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} is missing and could not be built ({err}): build it with "
+                "`python -m portfoliooptgp_b200.build` (nvcc, sm_100a).  There is no CPU fallback on this path.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
