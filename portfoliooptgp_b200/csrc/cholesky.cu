@@ -14,6 +14,14 @@
 // Every O(N^3) flop runs in dgemm.cu on the FP64 tensor pipe; the only non-GEMM work is the
 // 128x128 leaf (block_chol.cuh), one CTA, latency-bound.
 // Flops: factor N^3/3 + inverse N^3/3 + lauum N^3/3 = N^3.
+//
+// Round 2, in this file as well:
+//   factor_inv_chain      the bottom of the recursion (diagonal blocks <= 1024 rows) as a look-ahead chain over
+//                         the 128-row leaves: the next leaf waits for one panel product and one 128-column update
+//   factor_L, solve_L_*   factor ONLY (N^3/3 flop) for value-only / predict-only flows (GPR/predictor.py:6,
+//                         Multi-Input_GPR/main.py:434, BASELINE config C4), block substitution with the inverses of
+//                         the 1024-row diagonal blocks only
+//   factor_inv_pipelined  right-looking variant over two SM partitions (partition.cu); measured slower, opt-in
 #include <stdlib.h>
 
 #include "block_chol.cuh"
