@@ -179,7 +179,7 @@ int gpb_create(gpb_handle** out, int device) {
         cudaEventCreateWithFlags(&h->ev_fork[d], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_join[d], cudaEventDisableTiming);
     }
-    partitions_create(h);
+    // (the SM partitions of the opt-in pipelined factorisation are created when option 4 is switched on)
     *out = h;
     return 0;
 }
@@ -230,7 +230,15 @@ int gpb_set_option(gpb_handle* h, int option, int value) {
         case 0: h->fork_streams = (value != 0); return 0;
         case 1: h->use_pdl = (value != 0); return 0;
         case 2: h->use_shapes = (value != 0); return 0;
-        case 4: h->use_pipeline = (value != 0); return 0;
+        case 4: {
+            h->use_pipeline = (value != 0);
+            if (h->use_pipeline && !h->part_ok && !h->part_tried) {
+                DeviceGuard guard(h->device);
+                h->part_tried = true;
+                partitions_create(h);
+            }
+            return 0;
+        }
         case 5: h->use_chain = (value != 0); return 0;
         case 3:
             if (value < 0 || value > 2) return set_error(h, -2, "option 3 (objective refinement) takes 0, 1 or 2");

@@ -26,6 +26,7 @@ struct gpb_handle {
     // what it was computed for, and whether the workspaces still hold it (any other use of BUF_K / BUF_W /
     // BUF_VEC clears the flag).  fact_serial counts factorisations; gpb_gpr_predict_f_reuse consumes it.
     bool fact_valid = false;
+    bool alpha_valid = false;   // BUF_VEC holds alpha = (K + s2 I)^-1 y of the stored factorisation (gpb_gpr_get_alpha)
     int fact_kind = 0;          // 1: W = L^-1 in BUF_W (factor_inv); 2: factor only -- L in BUF_K (diagonal blocks) / BUF_W, block inverses in BUF_WD
     int64_t fact_serial = 0;
     const double* fact_X = nullptr;
@@ -39,6 +40,7 @@ struct gpb_handle {
     // SM partitions (green contexts, partition.cu) for the pipelined factorisation: streams of the bulk
     // partition and of the small critical-chain partition; gpb_set_option(h, 4, x) switches the pipeline
     bool part_ok = false;
+    bool part_tried = false;
     bool use_chain = true;      // gpb_set_option(h, 5, x): look-ahead chain over the 128-row leaves of a <= 1024-row diagonal block
     bool use_pipeline = false;  // measured slower than the recursion (profiles/r02_pipeline_ab.txt): opt-in
     cudaStream_t part_bulk = nullptr, part_crit = nullptr;

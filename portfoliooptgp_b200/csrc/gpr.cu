@@ -68,8 +68,9 @@ static bool factor_matches(const gpb_handle* h, bool was_valid, const double* th
     return memcmp(h->fact_theta, theta, sizeof(double) * (size_t)h->spec.n_params) == 0;
 }
 
-static void factor_remember(gpb_handle* h, const double* theta, double noise, int kind) {
+static void factor_remember(gpb_handle* h, const double* theta, double noise, int kind, bool has_alpha = true) {
     h->fact_valid = true;
+    h->alpha_valid = has_alpha;
     h->fact_kind = kind;
     h->fact_serial += 1;
     h->fact_X = h->d_X; h->fact_N = h->N; h->fact_D = h->D; h->fact_noise = noise;
@@ -234,7 +235,7 @@ int gpr_lml(gpb_handle* h, const double* theta, double noise, double* lml, doubl
         if ((rc = gpr_wd(h, &w))) return rc;
         if ((rc = gpr_factor_only(h, kp, noise, w))) return rc;
         if (refine && (rc = gpr_refine_objective(h, kp, noise, w, 2))) return rc;
-        factor_remember(h, theta, noise, 2);
+        factor_remember(h, theta, noise, 2, refine);   // the value-only flow forms alpha only when it refines
     }
     // one D2H of [quad, logdet, g_0..g_P] + info, then the only sync of the evaluation
     double* hp = pinned(h, (size_t)(64 + 2) * sizeof(double));
@@ -282,6 +283,7 @@ int gpr_predict_f(gpb_handle* h, const double* theta, double noise, const double
     }
     if (reuse) h->fact_valid = true;        // same factorisation, same serial
     else factor_remember(h, theta, noise, 2);
+    h->alpha_valid = true;                  // (both branches below leave alpha in place)
     const int64_t N = h->N;
     if (kind == 2 && (rc = solve_LT_vec(h, w.W, w.ld, w.Wd, N, w.a, w.alpha, w.tmp))) return rc;
     // chunk the test points so that the two [N, chunk] work matrices stay near 1 GiB each
@@ -346,6 +348,8 @@ namespace gpb {
 // (= d LML / d m(X): what the host layer needs to train mean-function parameters).
 int gpr_get_alpha(gpb_handle* h, double* d_alpha) {
     if (!h->d_X || h->N <= 0) return set_error(h, -3, "get_alpha: no data bound");
+    if (!h->fact_valid || !h->alpha_valid)
+        return set_error(h, -3, "get_alpha: no alpha held (call gpb_gpr_lml_grad or gpb_gpr_predict_f on this handle first)");
     GprWork w;
     const bool keep = h->fact_valid;   // read-only use of the workspaces
     int rc = gpr_workspaces(h, &w);

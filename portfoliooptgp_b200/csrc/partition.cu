@@ -55,7 +55,8 @@ const DriverApi& driver() {
 }
 }  // namespace
 
-// Called from gpb_create with the handle's device current.  Never fails the handle.
+// Called (once per handle) when the pipelined factorisation is switched on, with the handle's device current.
+// Never fails the handle.
 void partitions_create(gpb_handle* h) {
     h->part_ok = false;
     const char* off = getenv("GPB_NO_PARTITIONS");
