@@ -483,6 +483,26 @@ def bench_c1(gpflow, torch):
         except Exception as e:
             out[tag] = {"error": repr(e)[:200]}
     out["workload"] = "C1: N=1000, D=1, SE+Periodic(SE), Scipy L-BFGS-B maxiter=100 + predict_f (wall clock, host loop included)"
+    # the reference's R1 loop at this size: the 8 candidate kernels of GPR/main.py:105-114, each fitted (maxiter 100)
+    # + in-sample predict_f + MSE select (GPR/model_trainer.py:10-26), one after the other vs four fits in flight
+    try:
+        def cands():
+            return [K.SquaredExponential(), K.Matern12(), K.RationalQuadratic(), K.Exponential(), K.SquaredExponential() + K.Matern12(),
+                    K.Exponential() + K.Periodic(K.SquaredExponential()) + K.Linear(), K.Exponential() + K.Periodic(K.SquaredExponential()),
+                    K.SquaredExponential() * K.Matern12()]
+        gpflow.GPRModelTrainer(cands()[:2], max_workers=2).train_model(X[:200], Y[:200])   # warm the worker handles
+        r = {}
+        for tag, w in (("sequential", 1), ("four_in_flight", 4)):
+            ks = cands()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            bk, bmse, bm = gpflow.GPRModelTrainer(ks, max_workers=w).train_model(X, Y)
+            torch.cuda.synchronize()
+            r[tag] = {"seconds": time.perf_counter() - t0, "best_kernel": type(bk).__name__, "best_mse": bmse}
+        r["speedup"] = r["sequential"]["seconds"] / r["four_in_flight"]["seconds"]
+        r["same_selection"] = (r["sequential"]["best_mse"] == r["four_in_flight"]["best_mse"])
+        out["r1_eight_candidates"] = r
+    except Exception as e:
+        out["r1_eight_candidates"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -17,3 +17,5 @@ from . import batched  # noqa: E402,F401
 from .batched import BatchedGPR, lockstep_lbfgsb  # noqa: E402,F401
 from . import data_prep, postprocess  # noqa: E402,F401
 from . import mean_functions as functions  # noqa: E402,F401  (gpflow.functions alias)
+from . import trainers  # noqa: E402,F401
+from .trainers import GPRModelTrainer, MultiInputModelTrainer, fit_concurrently  # noqa: E402,F401
