@@ -403,6 +403,10 @@ def run_gpu(args):
             extras["c5_svgp"] = {"error": repr(e)}
     if not args.no_extras and rank == 0 and world == 1:
         try:
+            extras["c2_concurrent_models"] = bench_c2_concurrent(gpflow, torch, k)
+        except Exception as e:
+            extras["c2_concurrent_models"] = {"error": repr(e)[:300]}
+        try:
             extras["c4_large_gp"] = bench_c4(gpflow, torch)
         except Exception as e:
             extras["c4_large_gp"] = {"error": repr(e)[:300]}
@@ -595,6 +599,27 @@ def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
             "full_fits_per_s": total / fit_s, "full_fit_s": fit_s, "fit_mean_iterations": nit,
             "fit_converged_fraction": conv, "parity_sample": parity,
             "fit_note": "lock-step SciPy L-BFGS-B on the host (bit-identical iterates), LML+grad on the device"}
+
+
+def bench_c2_concurrent(gpflow, torch, kernel, evals=6):
+    """The headline evaluation with several INDEPENDENT models in flight on one GPU (restarts / kernel candidates:
+    models/model_trainer.py:26-48, GPR/main.py:105-114), one host thread + engine handle + CUDA stream each
+    (portfoliooptgp_b200.trainers.run_concurrently).  `value` above stays the one-model-at-a-time figure."""
+    from portfoliooptgp_b200.trainers import run_concurrently
+    out = {"workload": "C2 evaluation (N=8192, D=8), k independent models in flight; aggregate LML+grad evals/s"}
+    for kk in (1, 2, 4):
+        models = [gpflow.models.GPR(make_c2(seed=20 + i), kernel=kernel, noise_variance=NOISE_C2) for i in range(kk)]
+        tasks = [(lambda mm=mm: [mm.lml_and_constrained_grads() for _ in range(evals)]) for mm in models]
+        warm = [(lambda mm=mm: mm.lml_and_constrained_grads()) for mm in models]
+        run_concurrently(warm, models[0]._device_index, models_of_task=[[mm] for mm in models], max_workers=kk)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_concurrently(tasks, models[0]._device_index, models_of_task=[[mm] for mm in models], max_workers=kk)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[str(kk)] = {"evals_per_s": kk * evals / dt, "ms_per_eval_aggregate": 1e3 * dt / (kk * evals)}
+        del models
+    return out
 
 
 def bench_c4(gpflow, torch):
