@@ -72,7 +72,7 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     the iterates stay bit-identical to SciPy's."""
     _lb = _scipy_lbfgsb_module()
     if workers and workers > 1 and len(X0) >= 4 * workers:
-        return _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, int(workers))
+        return _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, int(workers), fun_batch_async)
     _lbfgsb = _lb._lbfgsb
     int_dtype = np.int64 if getattr(_lb, "HAS_ILP64", False) else np.int32
     X0 = np.ascontiguousarray(X0, dtype=np.float64)
@@ -191,10 +191,12 @@ def lockstep_lbfgsb(fun_batch: Callable[[np.ndarray, np.ndarray], Tuple[np.ndarr
     return results
 
 
-def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, workers):
+def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol, maxls, workers, fun_batch_async=None):
     """lockstep_lbfgsb with the per-problem setulb calls spread over worker processes (_lbfgsb_pool):
-    the same call sequence per problem, so the same iterates; only the host time per round shrinks."""
-    from scipy.optimize import _lbfgsb_py as _lb
+    the same call sequence per problem, so the same iterates; only the host time per round shrinks.
+    With ``fun_batch_async`` and >= 4 workers the workers form two groups that alternate: while one group's
+    problems are evaluated on the device the other group's processes advance their SciPy state machines."""
+    _lb = _scipy_lbfgsb_module()
     from . import _lbfgsb_pool
     X0 = np.ascontiguousarray(X0, dtype=np.float64)
     B, n = X0.shape
@@ -204,22 +206,62 @@ def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol,
     for w, wk in enumerate(pool):
         wk.send(("init", X0[bounds[w]:bounds[w + 1]], maxcor, factr, gtol, maxls, maxiter, maxfun))
     replies = [wk.recv() for wk in pool]
-    while True:
-        counts = [len(r[0]) for r in replies]
-        if sum(counts) == 0:
-            break
-        idx = np.concatenate([r[0] + bounds[w] for w, r in enumerate(replies)])
-        Xb = np.concatenate([r[1] for r in replies], axis=0)
-        fb, gb = fun_batch(Xb, idx)
+    two_groups = fun_batch_async is not None and workers >= 4
+    groups = [list(range(0, workers // 2)), list(range(workers // 2, workers))] if two_groups else [list(range(workers))]
+
+    def gather(g):
+        counts = {w: len(replies[w][0]) for w in g}
+        if sum(counts.values()) == 0:
+            return None
+        idx = np.concatenate([replies[w][0] + bounds[w] for w in g])
+        Xb = np.concatenate([replies[w][1] for w in g], axis=0)
+        return counts, idx, Xb
+
+    def scatter(g, counts, fb, gb):
         fb = np.asarray(fb, dtype=np.float64)
         gb = np.asarray(gb, dtype=np.float64)
         o = 0
-        for w, wk in enumerate(pool):
+        for w in g:
             c = counts[w]
             if c:
-                wk.send(("step", fb[o:o + c], gb[o:o + c]))
+                pool[w].send(("step", fb[o:o + c], gb[o:o + c]))
             o += c
-        replies = [wk.recv() if counts[w] else replies[w] for w, wk in enumerate(pool)]
+
+    def collect(g, counts):
+        for w in g:
+            if counts[w]:
+                replies[w] = pool[w].recv()
+
+    if not two_groups:
+        while True:
+            got = gather(groups[0])
+            if got is None:
+                break
+            counts, idx, Xb = got
+            fb, gb = fun_batch(Xb, idx)
+            scatter(groups[0], counts, fb, gb)
+            collect(groups[0], counts)
+    else:
+        pend = [None, None]      # per group: (counts, wait) of the evaluation in flight
+        for gi, g in enumerate(groups):
+            got = gather(g)
+            if got is not None:
+                pend[gi] = (got[0], fun_batch_async(got[2], got[1]))
+        while pend[0] is not None or pend[1] is not None:
+            sent = [None, None]
+            for gi, g in enumerate(groups):          # results back to the workers: they start advancing at once
+                if pend[gi] is not None:
+                    counts, wait = pend[gi]
+                    fb, gb = wait()
+                    scatter(g, counts, fb, gb)
+                    sent[gi] = counts
+                    pend[gi] = None
+            for gi, g in enumerate(groups):          # next evaluation of a group starts while the other one advances
+                if sent[gi] is not None:
+                    collect(g, sent[gi])
+                    got = gather(g)
+                    if got is not None:
+                        pend[gi] = (got[0], fun_batch_async(got[2], got[1]))
     results = []
     for wk in pool:
         wk.send(("finish",))
@@ -438,9 +480,30 @@ class BatchedGPR:
 
         return wait
 
+    @staticmethod
+    def default_workers(B: int) -> int:
+        """Worker processes for the host side of a lock-step fit of B GPs: SciPy's ``setulb`` (GIL-bound, ~3 us
+        per problem and round) is most of a large fit, so batches of >= 2048 GPs spread it over the host cores
+        this rank may use (cores // ranks on the node - 1, at most 12); smaller batches stay in process."""
+        if B < 2048:
+            return 0
+        import os
+        world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size())))
+        except Exception:
+            pass
+        n = min(12, (os.cpu_count() or 1) // world - 1)
+        return n if n >= 2 else 0
+
     def fit(self, maxiter: int = 15000, **lbfgs_kwargs) -> List[scipy.optimize.OptimizeResult]:
         """Scipy().minimize(model.training_loss, model.trainable_variables) for every GP, lock step.
-        ``workers=k`` (k > 1) advances the SciPy state machines in k worker processes (same iterates)."""
+        ``workers=k`` (k > 1) advances the SciPy state machines in k worker processes (same iterates, bit for
+        bit); the default (``workers="auto"``) is ``default_workers(B)``."""
+        if lbfgs_kwargs.get("workers", "auto") == "auto":
+            lbfgs_kwargs["workers"] = self.default_workers(self.B)
         U0 = self._pack()
         self.non_pd_evaluations = np.zeros(self.B, dtype=np.int64)
         pipelined = lbfgs_kwargs.pop("pipelined", self.B >= 64)

@@ -101,16 +101,31 @@ def test_lockstep_workers_reproduce_the_in_process_iterates():
         return 0.5 * np.sum(A[idx] * d * d, axis=1) + 0.1 * np.sum(d ** 4, axis=1) + np.sum(np.cos(d), axis=1), \
             A[idx] * d + 0.4 * d ** 3 - np.sin(d)
 
+    in_flight = []
+
+    def fun_async(U, idx):
+        U, idx = U.copy(), idx.copy()
+        in_flight.append(1)
+        assert len(in_flight) <= 2
+
+        def wait():
+            in_flight.pop()
+            return fun(U, idx)
+        return wait
+
     X0 = rng.normal(size=(B, n))
     r0 = lockstep_lbfgsb(fun, X0, maxiter=60)
     try:
         r1 = lockstep_lbfgsb(fun, X0, maxiter=60, workers=3)
+        # two groups of workers alternating: one group's evaluation in flight while the other group advances
+        r2 = lockstep_lbfgsb(fun, X0, maxiter=60, workers=4, fun_batch_async=fun_async)
     finally:
         _lbfgsb_pool.shutdown()
-    assert len(r1) == B
-    for a, b in zip(r0, r1):
-        assert np.array_equal(a.x, b.x) and a.fun == b.fun and np.array_equal(a.jac, b.jac)
-        assert (a.nit, a.nfev, a.status, a.message) == (b.nit, b.nfev, b.status, b.message)
+    assert len(r1) == B and len(r2) == B
+    for r in (r1, r2):
+        for a, b in zip(r0, r):
+            assert np.array_equal(a.x, b.x) and a.fun == b.fun and np.array_equal(a.jac, b.jac)
+            assert (a.nit, a.nfev, a.status, a.message) == (b.nit, b.nfev, b.status, b.message)
 
 
 def test_pipelined_halves_give_the_same_iterates():
