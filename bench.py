@@ -603,7 +603,7 @@ def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
             "full_fits_per_s": total / fit_s, "full_fit_s": fit_s, "fit_mean_iterations": nit,
             "fit_converged_fraction": conv, "parity_sample": parity,
             "fit_host_workers": nw,
-            "fit_note": "lock-step SciPy L-BFGS-B on the host (bit-identical iterates; worker processes for the SciPy state machines when the shard has >= 4096 GPs), LML+grad on the device"}
+            "fit_note": "lock-step SciPy L-BFGS-B on the host (bit-identical iterates; worker processes for the SciPy state machines when the shard has >= 512 GPs), LML+grad on the device"}
 
 
 def bench_c2_concurrent(gpflow, torch, kernel, evals=6):

@@ -87,6 +87,8 @@ while True:
     elif op == "finish":
         send((st["X"], st["F"], st["G"], st["TASK"], st["NIT"], st["NFEV"]))
         st = None
+    elif op == "ping":
+        send(("pong",))
     elif op == "quit":
         sys.exit(0)
 '''
@@ -111,6 +113,10 @@ class _Worker:
         (n,) = struct.unpack("<Q", h)
         return pickle.loads(self.p.stdout.read(n))
 
+    def fileno(self) -> int:
+        """for select(): a reply is waiting (replies are read whole, so nothing stays in Python's buffer)"""
+        return self.p.stdout.fileno()
+
     def close(self):
         try:
             if self.p.poll() is None:
@@ -128,9 +134,16 @@ _pool: List[_Worker] = []
 
 
 def get_workers(n: int) -> List[_Worker]:
-    """A persistent pool (start-up costs an interpreter + numpy/scipy import per worker, ~0.5 s in parallel)."""
+    """A persistent pool (start-up costs an interpreter + numpy/scipy import per worker, ~0.5 s in parallel).
+    New workers are pinged, so the pool is ready (imports done) when this returns."""
+    fresh = []
     while len(_pool) < n:
         _pool.append(_Worker())
+        fresh.append(_pool[-1])
+    for wk in fresh:
+        wk.send(("ping",))
+    for wk in fresh:
+        wk.recv()
     return _pool[:n]
 
 

@@ -15,6 +15,8 @@ evaluation and one final gather (``shard_range`` / ``gather_results``; SURVEY.md
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -206,8 +208,12 @@ def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol,
     for w, wk in enumerate(pool):
         wk.send(("init", X0[bounds[w]:bounds[w + 1]], maxcor, factr, gtol, maxls, maxiter, maxfun))
     replies = [wk.recv() for wk in pool]
-    two_groups = fun_batch_async is not None and workers >= 4
-    groups = [list(range(0, workers // 2)), list(range(workers // 2, workers))] if two_groups else [list(range(workers))]
+    pipelined = fun_batch_async is not None and workers >= 4
+    ngroups = (4 if workers >= 12 else 3 if workers >= 9 else 2) if pipelined else 1
+    if pipelined and os.environ.get("GPB_FIT_GROUPS"):       # tuning knob (tools/c3_fit.py)
+        ngroups = max(2, min(workers // 2, int(os.environ["GPB_FIT_GROUPS"])))
+    cuts = [(workers * g) // ngroups for g in range(ngroups + 1)]
+    groups = [list(range(cuts[g], cuts[g + 1])) for g in range(ngroups)]
 
     def gather(g):
         counts = {w: len(replies[w][0]) for w in g}
@@ -227,12 +233,7 @@ def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol,
                 pool[w].send(("step", fb[o:o + c], gb[o:o + c]))
             o += c
 
-    def collect(g, counts):
-        for w in g:
-            if counts[w]:
-                replies[w] = pool[w].recv()
-
-    if not two_groups:
+    if not pipelined:
         while True:
             got = gather(groups[0])
             if got is None:
@@ -240,28 +241,52 @@ def _lockstep_lbfgsb_workers(fun_batch, X0, maxiter, maxfun, maxcor, ftol, gtol,
             counts, idx, Xb = got
             fb, gb = fun_batch(Xb, idx)
             scatter(groups[0], counts, fb, gb)
-            collect(groups[0], counts)
+            for w in groups[0]:
+                if counts[w]:
+                    replies[w] = pool[w].recv()
     else:
-        pend = [None, None]      # per group: (counts, wait) of the evaluation in flight
-        for gi, g in enumerate(groups):
-            got = gather(g)
-            if got is not None:
-                pend[gi] = (got[0], fun_batch_async(got[2], got[1]))
-        while pend[0] is not None or pend[1] is not None:
-            sent = [None, None]
-            for gi, g in enumerate(groups):          # results back to the workers: they start advancing at once
-                if pend[gi] is not None:
-                    counts, wait = pend[gi]
-                    fb, gb = wait()
-                    scatter(g, counts, fb, gb)
-                    sent[gi] = counts
-                    pend[gi] = None
-            for gi, g in enumerate(groups):          # next evaluation of a group starts while the other one advances
-                if sent[gi] is not None:
-                    collect(g, sent[gi])
-                    got = gather(g)
-                    if got is not None:
-                        pend[gi] = (got[0], fun_batch_async(got[2], got[1]))
+        # Event-driven: every group is either on the device (an evaluation in flight) or on the host (its
+        # processes advancing); the parent serves whichever is ready, so one group's device time hides behind
+        # the other groups' host time and nobody waits at the head of a fixed order.
+        import select
+        EVAL, ADV, DONE = 0, 1, 2
+        state = [DONE] * ngroups
+        info = [None] * ngroups
+
+        def launch(gi):
+            got = gather(groups[gi])
+            if got is None:
+                state[gi], info[gi] = DONE, None
+            else:
+                state[gi], info[gi] = EVAL, (got[0], fun_batch_async(got[2], got[1]))
+
+        for gi in range(ngroups):
+            launch(gi)
+        while any(st != DONE for st in state):
+            progressed = False
+            for gi in range(ngroups):
+                if state[gi] == EVAL:
+                    counts, wait = info[gi]
+                    if getattr(wait, "ready", None) is None or wait.ready():
+                        fb, gb = wait()
+                        scatter(groups[gi], counts, fb, gb)
+                        state[gi], info[gi] = ADV, {w for w in groups[gi] if counts[w]}
+                        progressed = True
+                elif state[gi] == ADV:
+                    waiting = info[gi]
+                    ready, _, _ = select.select([pool[w] for w in waiting], [], [], 0)
+                    for wk in ready:
+                        w = pool.index(wk)
+                        replies[w] = wk.recv()
+                        waiting.discard(w)
+                    if not waiting:
+                        launch(gi)
+                        progressed = True
+            if not progressed:
+                # nothing ready: block briefly on the worker pipes of the advancing groups (or yield)
+                fds = [pool[w] for gi in range(ngroups) if state[gi] == ADV for w in info[gi]]
+                if fds:
+                    select.select(fds, [], [], 2e-4)
     results = []
     for wk in pool:
         wk.send(("finish",))
@@ -365,10 +390,9 @@ class BatchedGPR:
         self._engine = ops.shared_engine(self.device_index)
         self._out = torch.empty((self.B, 2 + self.P), dtype=torch.float64, device=self.X.device)
         self._info = torch.zeros((self.B,), dtype=torch.int32, device=self.X.device)
-        # second result set for the pipelined fit (two half-batches in flight, lockstep_lbfgsb)
-        self._out2 = None
-        self._info2 = None
-        self._flip = 0
+        # further result sets for the pipelined fit (several part-batches in flight, lockstep_lbfgsb)
+        self._more_out = {}
+        self._slot_busy = [False]
 
     # -- raw device evaluation ---------------------------------------------------------------------
     def _launch(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool, slot: int = 0):
@@ -389,9 +413,9 @@ class BatchedGPR:
         if slot == 0:
             out, info = self._out[:b], self._info[:b]
         else:
-            if self._out2 is None:
-                self._out2, self._info2 = torch.empty_like(self._out), torch.zeros_like(self._info)
-            out, info = self._out2[:b], self._info2[:b]
+            if slot not in self._more_out:
+                self._more_out[slot] = (torch.empty_like(self._out), torch.zeros_like(self._info))
+            out, info = self._more_out[slot][0][:b], self._more_out[slot][1][:b]
         eng.batched_lml_grad(Xb.data_ptr(), Yb.data_ptr(), th.data_ptr(), nz.data_ptr(), b, self.N, self.D,
                              out.data_ptr(), info.data_ptr(), want_grad, None if nr is None else nr.data_ptr())
         # (the inputs th, nz, Xb, Yb stay referenced by the caller-visible tensors of this stream-ordered launch;
@@ -462,13 +486,17 @@ class BatchedGPR:
         return self._finish_unconstrained(U, idx, lml, gth, gnz, info)
 
     def loss_and_grads_unconstrained_async(self, U: np.ndarray, idx: np.ndarray):
-        """Start the evaluation (H2D copies and the kernel go onto the stream) and return ``wait() -> (f, g)``;
-        two evaluations may be in flight (alternating result buffers)."""
+        """Start the evaluation (H2D copies and the kernel go onto the stream) and return ``wait() -> (f, g)``
+        (``wait.ready()`` tells whether it would block); several evaluations may be in flight, each with its
+        own result buffers."""
         U = np.array(U, dtype=np.float64)
         idx = np.array(idx, dtype=np.int64)
         theta, noise = self._unpack(U, idx)
-        slot = self._flip
-        self._flip ^= 1
+        slot = next((s for s, busy in enumerate(self._slot_busy) if not busy), None)
+        if slot is None:
+            slot = len(self._slot_busy)
+            self._slot_busy.append(False)
+        self._slot_busy[slot] = True
         out, info = self._launch(theta, noise, idx, True, slot=slot)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.X.device))
@@ -476,18 +504,20 @@ class BatchedGPR:
         def wait():
             ev.synchronize()
             o = out.cpu().numpy()
-            return self._finish_unconstrained(U, idx, o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), info.cpu().numpy())
+            inf = info.cpu().numpy()
+            self._slot_busy[slot] = False
+            return self._finish_unconstrained(U, idx, o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), inf)
 
+        wait.ready = ev.query
         return wait
 
     @staticmethod
     def default_workers(B: int) -> int:
         """Worker processes for the host side of a lock-step fit of B GPs: SciPy's ``setulb`` (GIL-bound, ~3 us
-        per problem and round) is most of a large fit, so batches of >= 4096 GPs spread it over the host cores
+        per problem and round) is most of a large fit, so batches of >= 512 GPs spread it over the host cores
         this rank may use (cores // ranks on the node - 1, at most 12); smaller batches stay in process
-        (measured: 5120 GPs 3620 -> 5020 fits/s with 12 workers; 2560 GPs per rank 6600 in process vs 6420
-        with workers, the pipes cost what the processes save)."""
-        if B < 4096:
+        (measured on one B200, 5120 GPs: 3620 fits/s in process, 12 700 with 12 workers in four groups)."""
+        if B < 512:
             return 0
         import os
         world = 1
