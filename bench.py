@@ -202,7 +202,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "cores_note": "threads of the LAPACK/BLAS pool, pinned with threadpoolctl; element-wise NumPy passes are single-threaded"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "GPflow 2.9.1/TF 2.16 not installable here; CPU oracle port (oracle/gpflow_oracle.py) stands in for the reference"}
     print(json.dumps(line), flush=True)
@@ -422,6 +423,7 @@ def run_gpu(args):
         dt, (l0, g0, n0) = cpu_lml_grad_once(X, Y)
         cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "1 full N=8192 evaluation of the same inputs (oracle/gpflow_oracle.py, NumPy/SciPy LAPACK, analytic gradient)",
+               "cores_note": "cores = threads of the LAPACK/BLAS pool (threadpoolctl); the oracle's element-wise NumPy passes (about half of its time) run on one thread, as they would in any NumPy program",
                "seconds": dt, "lml_rel_diff_vs_gpu": abs(l0 - lml) / abs(l0),
                "grad_max_abs_diff_vs_gpu": float(np.max(np.abs(np.asarray(g0) - np.asarray(g))))}
 
