@@ -160,9 +160,12 @@ __host__ __device__ constexpr int gram_groups_of() {
 }
 
 // resident CTAs per SM to compile for: single-leaf straight-line kernels fit 64 registers
+#ifndef GPB_GRAM_BLOCKS_1LEAF
+#define GPB_GRAM_BLOCKS_1LEAF 4
+#endif
 template <class SH>
 __host__ __device__ constexpr int gram_min_blocks() {
-    if constexpr (SH::is_static) return SH::NL == 1 ? 4 : 3;
+    if constexpr (SH::is_static) return SH::NL == 1 ? GPB_GRAM_BLOCKS_1LEAF : 3;
     else return 3;
 }
 
