@@ -197,7 +197,6 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
     double* Bs = gsm + L::B;
     double* na = gsm + L::NA;
     double* nb = gsm + L::NB_;
-    double* stage = gsm + L::STAGE;
 
     int ti, tj;
     if (mode == 0) {
@@ -401,9 +400,13 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                 if (r == cc) v0 += diag_add;
                 if (r == cc + 1) v1 += diag_add;
             }
-            if (mode == 2) {
-                stage[r * TILE + ((cc + r) & (TILE - 1))] = v0;
-                stage[r * TILE + ((cc + 1 + r) & (TILE - 1))] = v1;
+            if (mode == 2 && ti != tj && gi < N) {
+                // mirrored copy straight from the registers: for a fixed column the 8 rows of a warp's g-lanes are
+                // 8 consecutive doubles of the transposed row, i.e. every 32-byte sector is written whole (no
+                // staging tile, no barrier: the staged mirror cost 25 % of the kernel)
+                const int64_t gjm = col0 + cc;
+                if (gjm < N) Kout[gjm * ldk + gi] = v0;
+                if (gjm + 1 < N) Kout[(gjm + 1) * ldk + gi] = v1;
             }
             if (gi < N) {
                 const int64_t gj = col0 + cc;
@@ -413,27 +416,6 @@ assemble_gram_kernel(const __grid_constant__ DevKernel kp, const double* __restr
                 } else {
                     if (gj < N2) p[0] = v0;
                     if (gj + 1 < N2) p[1] = v1;
-                }
-            }
-        }
-    }
-    if (mode == 2 && ti != tj) {
-        __syncthreads();
-        const int tx = tid & 31, ty = tid >> 5, c0 = 2 * tx;
-#pragma unroll 1
-        for (int rr = 0; rr < ROWS_PT; ++rr) {
-            const int rw = ty * ROWS_PT + rr;
-            const int64_t gi = col0 + rw;
-            if (gi < N) {
-                const int64_t gj = row0 + c0;
-                const double v0 = stage[c0 * TILE + ((rw + c0) & (TILE - 1))];
-                const double v1 = stage[(c0 + 1) * TILE + ((rw + c0 + 1) & (TILE - 1))];
-                double* p = Kout + gi * ldk + gj;
-                if (vec_ok && gj + 1 < N) {
-                    *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
-                } else {
-                    if (gj < N) p[0] = v0;
-                    if (gj + 1 < N) p[1] = v1;
                 }
             }
         }
@@ -608,7 +590,7 @@ int launch_assemble(gpb_handle* h, const DevKernel& kp, const double* d_X, int64
         using SHL = GPB_SH_FOR(DPV);                                                                                     \
         using GS = GramSmem<DPV, gram_groups_of<SHL>()>;                                                                 \
         constexpr int SM = GS::TOTAL * (int)sizeof(double);                                                              \
-        const int sm_now = (mode == 2 ? GS::TOTAL : GS::STAGE) * (int)sizeof(double);                                    \
+        const int sm_now = GS::STAGE * (int)sizeof(double);   /* (no mirror staging tile any more) */                    \
         e = ensure_dyn_smem(attr_set, h->device, assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)>, (size_t)SM);                \
         if (e == cudaSuccess)                                                                                            \
             assemble_gram_kernel<DPV, GPB_SH_FOR(DPV)><<<(unsigned)nblk, ASM_THREADS, sm_now, h->stream>>>(              \
