@@ -90,7 +90,7 @@ __device__ __forceinline__ void warp_mma_2x2(double (&c)[2][2][2], const double*
 //   (a) warp 0 factors the 8x8 diagonal block and inverts the factor, entirely in registers
 //       (every lane redundantly: no shuffles on the pivot chain), stores L_pp and M = L_pp^-1;
 //   (b) panel  <- panel * M^T        one DMMA tile product per 8 rows;
-//   (c) trailing update C -= P P^T   DMMA tiles of the lower triangle, held in registers across panels.
+//   (c) trailing update C -= P P^T   DMMA tiles of the lower triangle; left-looking per tile row (below).
 // Warp 0 owns the chain diagonal block -> panel tile 0 -> next diagonal block; the other warps run (b)
 // and (c) in a separate loop (block_potrf_lower below).
 // On exit the lower triangle holds L, the strict upper triangle of every 8x8 diagonal block is zero
@@ -244,47 +244,26 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
     // uncontended (measured: the in-situ diagonal factor was 35 % slower than the isolated one).
     const int aw = warp - 1 - (warp >> 2), naw = nwarps - ((nwarps + 3) >> 2);   // index among the updating warps
     const bool upd_warp = (warp & 3) != 0;
-    const int st_all = (nt8 + 1) >> 1, nst_all = st_all * (st_all + 1) / 2;
-    constexpr int OWN = 3;
-    // Trailing matrix in REGISTERS (12 or more updating warps): every updating warp owns up to three fixed
-    // 16x16 super-tiles (2x2 DMMA tiles) of the lower triangle for the whole factorisation and keeps their
-    // accumulators in registers across the panels; per panel it only reads the two panel fragments from
-    // shared memory.  A tile goes back to shared memory once, right after its last update: column-(k+1)
-    // tiles after panel k (they are the next panel), the diagonal tile (k+2, k+2) after panel k (warp 0
-    // applies its last update itself, in the look-ahead).  The C tiles were two thirds of the shared-memory
-    // traffic of the update, which bounded the first panels (tools/leaf_prof.cu).
-    const bool reg_path = nst_all <= OWN * naw;
-    int ownI[OWN], ownJ[OWN];
-    double acc[OWN][2][2][2];
-    if (reg_path && upd_warp) {
+    // LEFT-LOOKING update (seven or more updating warps): a warp owns one or two tile ROWS (i = 2 + aw, 2 + aw + naw).
+    // In step k it (B) applies the newest panel to its tile (i, k+1), which it has carried in registers since the
+    // step before, and stores it -- column k+1 is the next panel --, then (C) builds tile (i, k+2) from the stored
+    // original and ALL panels 0..k in one product of depth 8 (k + 1) and keeps it for the next step (the diagonal
+    // tile (k+2, k+2) goes back to shared memory: warp 0 applies its last update in the look-ahead).
+    // Against the right-looking schedule (every tile visited by every panel): the work of a step is one short
+    // and one deep product per warp instead of up to twelve depth-8 ones, so it no longer outlasts warp 0's
+    // pivot chain in the first half of the factorisation (tools/leaf_prof.cu: warp 0 waited 8-10 K of 43 K
+    // cycles at the end-of-step barrier), and a tile is loaded and stored once.
+    const bool left_path = (nt8 - 2) <= 2 * naw;
+    int rowS[2] = {nt8, nt8};
+    double2 accB[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    if (left_path && upd_warp) {
 #pragma unroll
-        for (int s_ = 0; s_ < OWN; ++s_) {
-            // u-th super-tile in the order J descending (longest-lived first), I ascending: dealt round robin
-            const int u = aw + s_ * naw;
-            int I = -1, J = -1;
-            if (u < nst_all) {
-                int base = 0;
-                for (int jj = st_all - 1; jj >= 0; --jj) {
-                    const int cnt = st_all - jj;
-                    if (u < base + cnt) { J = jj; I = jj + (u - base); break; }
-                    base += cnt;
-                }
+        for (int s_ = 0; s_ < 2; ++s_) {
+            const int i = 2 + aw + s_ * naw;
+            if (i < nt8) {
+                rowS[s_] = i;
+                accB[s_] = *reinterpret_cast<const double2*>(S + (i * 8 + g) * SLD + 8 + 2 * q);   // tile (i, 1), no panel yet
             }
-            ownI[s_] = I;
-            ownJ[s_] = J;
-#pragma unroll
-            for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                for (int rj = 0; rj < 2; ++rj) {
-                    const int ti = 2 * I + ri, tj = 2 * J + rj;
-                    // tiles this warp will ever update: column >= 1, on or below the diagonal, inside the matrix,
-                    // not the diagonal tiles (0,0), (1,1) (those only ever see warp 0)
-                    const bool mine = (I >= 0) && ti < nt8 && tj >= 1 && tj <= ti && !(ti == tj && tj <= 1);
-                    double2 cc = make_double2(0.0, 0.0);
-                    if (mine) cc = *reinterpret_cast<const double2*>(S + (ti * 8 + g) * SLD + tj * 8 + 2 * q);
-                    acc[s_][ri][rj][0] = cc.x;
-                    acc[s_][ri][rj][1] = cc.y;
-                }
         }
     }
     asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
@@ -297,39 +276,34 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
         GPB_POTRF_STAMP(1)
         asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
         GPB_POTRF_STAMP(2)
-        // (c) trailing update C -= P_ti P_tj^T over the 8x8 tiles (ti >= tj) right of the panel
-        if (upd_warp && reg_path) {
+        // (c) trailing update
+        if (upd_warp && left_path) {
 #pragma unroll
-            for (int s_ = 0; s_ < OWN; ++s_) {
-                const int I = ownI[s_], J = ownJ[s_];
-                if (I < 0 || 2 * J + 1 <= k) continue;   // no tile of this super-tile is right of panel k any more
-                const int ti0 = 2 * I, tj0 = 2 * J;
-                bool act[2][2];
-#pragma unroll
-                for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                    for (int rj = 0; rj < 2; ++rj) {
-                        const int ti = ti0 + ri, tj = tj0 + rj;
-                        act[ri][rj] = tj > k && tj <= ti && ti < nt8 && !(ti == tj && tj == k + 1);
+            for (int s_ = 0; s_ < 2; ++s_) {
+                const int i = rowS[s_];
+                if (i >= nt8 || i < k + 2) continue;        // no such row / row already factorised
+                // (B) last update of tile (i, k+1): -= P(i, k) P(k+1, k)^T
+                warp_tile_mma(accB[s_].x, accB[s_].y, S + (i * 8) * SLD + p, SLD, 1, S + ((k + 1) * 8) * SLD + p, 1, SLD, 8, -1.0);
+                *reinterpret_cast<double2*>(S + (i * 8 + g) * SLD + (k + 1) * 8 + 2 * q) = accB[s_];
+                // (C) tile (i, k+2) <- original - sum_{j <= k} P(i, j) P(k+2, j)^T   (two accumulator chains)
+                if (k + 2 < nt8) {
+                    double2 c = *reinterpret_cast<const double2*>(S + (i * 8 + g) * SLD + (k + 2) * 8 + 2 * q);
+                    double d0 = 0.0, d1 = 0.0;
+                    const double* ap = S + (i * 8 + g) * SLD + q;
+                    const double* bp = S + ((k + 2) * 8 + g) * SLD + q;
+#pragma unroll 2
+                    for (int kk = 0; kk < 8 * (k + 1); kk += 8) {
+                        dmma_8x8x4(c.x, c.y, -ap[kk], bp[kk]);
+                        dmma_8x8x4(d0, d1, -ap[kk + 4], bp[kk + 4]);
                     }
-                const bool a0 = act[0][0] || act[0][1], a1 = act[1][0] || act[1][1];
-                const bool b0 = act[0][0] || act[1][0], b1 = act[0][1] || act[1][1];
-                if (a0 || a1)
-                    warp_mma_2x2(acc[s_], S + (ti0 * 8) * SLD + p, SLD, 1, S + (tj0 * 8) * SLD + p, 1, SLD, 0, 8, -1.0, a0, a1,
-                                 b0, b1);
-#pragma unroll
-                for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                    for (int rj = 0; rj < 2; ++rj) {
-                        const int ti = ti0 + ri, tj = tj0 + rj;
-                        const bool last = act[ri][rj] && ((ti != tj && tj == k + 1) || (ti == tj && tj == k + 2));
-                        if (last)
-                            *reinterpret_cast<double2*>(S + (ti * 8 + g) * SLD + tj * 8 + 2 * q) =
-                                make_double2(acc[s_][ri][rj][0], acc[s_][ri][rj][1]);
-                    }
+                    c.x += d0;
+                    c.y += d1;
+                    if (i == k + 2) *reinterpret_cast<double2*>(S + (i * 8 + g) * SLD + (k + 2) * 8 + 2 * q) = c;
+                    else accB[s_] = c;
+                }
             }
         } else if (upd_warp) {
-            // fewer updating warps than the register scheme needs: C tiles stay in shared memory; 16x16
+            // fewer updating warps than the left-looking scheme needs: right-looking, C tiles in shared memory; 16x16
             // super-tiles (I >= J) of the trailing tile grid, one per warp and round; tile (0,0) belongs to
             // warp 0, tiles above the diagonal or past the edge are neither loaded nor stored
             const int o = p + 8, st = (mt + 1) >> 1, nst = st * (st + 1) / 2;
