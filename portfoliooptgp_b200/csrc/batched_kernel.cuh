@@ -123,18 +123,14 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
     __syncthreads();
     if (do_prof) prof[2] = clock64();
 
-    block_potrf_lower(S, np, fail, dinv);
+    block_potrf_inv(S, np, fail, dinv, T);   // L below the diagonal, W = L^-1 built beside it (block_chol.cuh)
     if (do_prof) prof[3] = clock64();
-    // log-det (fixed order) by warp 0
+    // log-det (fixed order) by warp 0 from the inverted diagonal blocks, beside the move of W by the other warps
     if (warp == 0) {
-        double s = 0.0;
-        for (int i = lane; i < N; i += 32) s += log(S[i * SLD + i]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        const double s = warp_logdiag_from_dinv(dinv, N);
         if (lane == 0) misc[10] = s;
     }
-    __syncthreads();
-    block_trtri_lower_inplace(S, np, T, dinv);   // S <- W = L^-1
+    block_w_to_lower(S, np, dinv, 1);            // S <- W = L^-1, row-major lower triangle
     if (do_prof) prof[4] = clock64();
 
     // ---- a = W y (warp per row), alpha = W^T a (thread per column)

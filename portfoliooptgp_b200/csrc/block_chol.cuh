@@ -22,6 +22,10 @@
 #define GPB_POTRF_STAMP(i)
 #endif
 
+#ifndef GPB_INV_LOOP_ROWS
+#define GPB_INV_LOOP_ROWS 14   // rows of the inverse built inside the factorisation loop (the rest right after it)
+#endif
+
 namespace gpb {
 
 constexpr int SLD = 132;          // shared-memory leading dimension (doubles)
@@ -180,7 +184,42 @@ __device__ __forceinline__ void warp_trailing_tile(double* S, int p, int t) {
     *reinterpret_cast<double2*>(C) = cc;
 }
 
-__device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* dinv) {
+// tile j of row r of W = L^-1 (j < r), given the rows above it and the inverted diagonal blocks:
+//   W[r, j] = -M_r ( L[r, j] M_j + sum_{l = j+1}^{r-1} L[r, l] W[l, j] )
+// W's off-diagonal tiles live TRANSPOSED in the unused upper triangle of S (W[a][b] at S[b * SLD + a]), its
+// diagonal blocks are the M_r in dinv: both operands of the sum are then k-contiguous rows of S (row block r
+// below the diagonal, row block j above it), one loop over the columns (j+1) 8 .. r 8.  scr: 8 x DLD doubles
+// of per-warp scratch (the product with M_r needs the sum as a B operand).
+__device__ __forceinline__ void warp_inv_tile(double* S, const double* dinv, double* scr, int r, int j) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
+    const double* ar = S + (r * 8 + g) * SLD + q;
+    const double* mj = dinv + j * 8 * DLD;
+    dmma_8x8x4(t0, t1, ar[j * 8], mj[q * DLD + g]);
+    dmma_8x8x4(u0, u1, ar[j * 8 + 4], mj[(4 + q) * DLD + g]);
+    const double* bj = S + (j * 8 + g) * SLD + q;
+#pragma unroll 2
+    for (int c = (j + 1) * 8; c < r * 8; c += 8) {
+        dmma_8x8x4(t0, t1, ar[c], bj[c]);
+        dmma_8x8x4(u0, u1, ar[c + 4], bj[c + 4]);
+    }
+    *reinterpret_cast<double2*>(scr + g * DLD + 2 * q) = make_double2(t0 + u0, t1 + u1);
+    __syncwarp();
+    const double* mr = dinv + r * 8 * DLD + g * DLD + q;
+    double r0 = 0.0, r1 = 0.0;
+    dmma_8x8x4(r0, r1, -mr[0], scr[q * DLD + g]);
+    dmma_8x8x4(r0, r1, -mr[4], scr[(4 + q) * DLD + g]);
+    __syncwarp();
+    S[(j * 8 + 2 * q) * SLD + r * 8 + g] = r0;
+    S[(j * 8 + 2 * q + 1) * SLD + r * 8 + g] = r1;
+}
+
+// INV = false: the factorisation alone.  INV = true (16 warps; T: 16 x 8 x DLD doubles of scratch): the rows of
+// W = L^-1 are built BESIDE the factorisation -- row k in step k, by the updating warps whose tile rows are
+// already factorised -- instead of by a separate recursive-doubling pass afterwards (14 K cycles at np = 128,
+// a third of the factorisation); on exit L is in the lower triangle as before, W as described at warp_inv_tile.
+template <bool INV>
+__device__ __forceinline__ void block_potrf_core(double* S, int np, int* fail, double* dinv, double* T) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -236,9 +275,7 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
             asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
             GPB_POTRF_STAMP(4)
         }
-        return;
-    }
-
+    } else {
     // Updating warps.  Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe (DMMA and DFMA issue to the same
     // unit): they only help with the panel products and sit the update out, so that the pivot chain runs
     // uncontended (measured: the in-situ diagonal factor was 35 % slower than the isolated one).
@@ -334,10 +371,73 @@ __device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, 
                                 make_double2(c[ri][rj][0], c[ri][rj][1]);
             }
         }
+        if (INV && upd_warp && k >= 1 && k <= GPB_INV_LOOP_ROWS) {
+            // row k of the inverse (M_k and the rows above are complete since the last barrier): tile j goes to
+            // the updating warp (k - 1 - j) mod naw -- warps whose tile rows are factorised; the deepest sum
+            // (j = 0) to the one that retired last
+            for (int j = k - 1 - aw; j >= 0; j -= naw) warp_inv_tile(S, dinv, T + warp * 8 * DLD, k, j);
+        }
         GPB_POTRF_STAMP(3)
         asm volatile("bar.sync 2, %0;" ::"r"(nt) : "memory");
         GPB_POTRF_STAMP(4)
     }
+    }
+    if (INV) {
+        // the remaining rows of the inverse: nothing left to run beside them, every warp takes tiles
+        for (int r = min(nt8 - 1, GPB_INV_LOOP_ROWS + 1); r < nt8; ++r) {
+            for (int j = warp; j < r; j += nwarps) warp_inv_tile(S, dinv, T + warp * 8 * DLD, r, j);
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void block_potrf_lower(double* S, int np, int* fail, double* dinv) {
+    block_potrf_core<false>(S, np, fail, dinv, nullptr);
+}
+
+// Factor and invert (blockDim.x = 512).  On exit: L in the lower triangle of S (diagonal blocks with a zero strict
+// upper part), dinv = the inverted diagonal blocks, and the off-diagonal tiles of W = L^-1 transposed above the
+// diagonal: W[a][b] = S[b * SLD + a] for a / 8 > b / 8, = dinv[(a / 8) * 8 * DLD + (a % 8) * DLD + b % 8] otherwise.
+__device__ __forceinline__ void block_potrf_inv(double* S, int np, int* fail, double* dinv, double* T) {
+    block_potrf_core<true>(S, np, fail, dinv, T);
+}
+
+// W (as left by block_potrf_inv) -> the lower triangle of S, row-major, overwriting L.  Tile by tile, a warp
+// per tile: lanes run along the contiguous direction of the source (two-way bank conflicts at most on either
+// side; an element-wise transposing copy has sixteen-way ones).
+// sum_i log L_ii over the first n rows from the inverted diagonal blocks (one warp, fixed order; result in lane 0)
+__device__ __forceinline__ double warp_logdiag_from_dinv(const double* dinv, int n) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s -= log(dinv[(i >> 3) * 8 * DLD + (i & 7) * (DLD + 1)]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// first_warp: warps below it take no part (the callers' warp 0 sums the log-diagonal meanwhile, from dinv --
+// log L_ii = -log M_ii --, which this pass only reads); all threads meet at the closing barrier.
+__device__ __forceinline__ void block_w_to_lower(double* S, int np, const double* dinv, int first_warp = 0) {
+    const int lane = threadIdx.x & 31, warp = (int)(threadIdx.x >> 5) - first_warp, nwarps = (int)(blockDim.x >> 5) - first_warp;
+    const int nt8 = np >> 3;
+    const int noff = nt8 * (nt8 - 1) / 2;
+    for (int t = (warp >= 0 ? warp : noff + nt8); t < noff + nt8; t += nwarps) {
+        if (t < noff) {
+            int a, j;
+            tri_tile(t, a, j);
+            const int r = a + 1;                      // tile (r, j), j < r
+            const int rr = lane & 7, c0 = lane >> 3;
+            const double v0 = S[(j * 8 + c0) * SLD + r * 8 + rr];
+            const double v1 = S[(j * 8 + c0 + 4) * SLD + r * 8 + rr];
+            S[(r * 8 + rr) * SLD + j * 8 + c0] = v0;
+            S[(r * 8 + rr) * SLD + j * 8 + c0 + 4] = v1;
+        } else {
+            const int r = t - noff, rr = lane >> 2, c2 = (lane & 3) * 2;
+            *reinterpret_cast<double2*>(S + (r * 8 + rr) * SLD + r * 8 + c2) =
+                *reinterpret_cast<const double2*>(dinv + r * 8 * DLD + rr * DLD + c2);
+        }
+    }
+    __syncthreads();
 }
 
 // ---- triangular inverse, in place ------------------------------------------------------------------------

@@ -66,7 +66,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
         }
     }
     __syncthreads();
-    block_potrf_lower(S, np, fail, dinv);
+    block_potrf_inv(S, np, fail, dinv, T);   // L below the diagonal, the tiles of W = L^-1 transposed above it
     if (tid == 0 && *fail != 0) atomicCAS(info, 0, info_base + offset + *fail);
     // L itself is only needed by callers that keep the factor (gpb_potrf, SVGP adjoint); the LML / K^-1
     // pipeline consumes W and the log-diagonal only, so the 128 KB store is skipped there
@@ -74,23 +74,21 @@ leaf_potrf_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ 
 #pragma unroll 8
         for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
             const int i = idx >> 7, j = idx & (NB - 1);
-            if (j < n) A[(int64_t)i * lda + j] = S[i * SLD + j];
+            if (j < n) A[(int64_t)i * lda + j] = (j <= i) ? S[i * SLD + j] : 0.0;
         }
     }
-    // sum of log-diagonal, fixed order: warp 0
+    // sum of the log-diagonal (fixed order, warp 0, from the inverted diagonal blocks) beside the move of W into
+    // row-major position by the other warps
+    if (store_L) __syncthreads();                 // L read out before W overwrites it
     if (tid < 32) {
-        double s = 0.0;
-        for (int i = tid; i < n; i += 32) s += log(S[i * SLD + i]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        const double s = warp_logdiag_from_dinv(dinv, n);
         if (tid == 0) logdiag[offset / NB] = s;
     }
-    __syncthreads();
-    block_trtri_lower_inplace(S, np, T, dinv);
+    block_w_to_lower(S, np, dinv, 1);
 #pragma unroll 8
     for (int idx = tid; idx < n * NB; idx += LEAF_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
-        if (j < n) W[(int64_t)i * ldw + j] = S[i * SLD + j];
+        if (j < n) W[(int64_t)i * ldw + j] = (j <= i) ? S[i * SLD + j] : 0.0;   // explicit zeros above the diagonal
     }
 }
 

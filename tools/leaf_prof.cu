@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(512) prof_kernel(const double* A, int n, long 
 
 // current production routines + isolated sub-phases (16 sequential diagonal factors; one full panel
 // product; one full trailing update at p = 0)
+template <int FUSED>
 __global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long long* stamps) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm; double* T = sm + 128 * SLD; double* dinv = T + 64 * TLD; int* fail = (int*)(dinv + DINV_DOUBLES);
@@ -134,10 +135,12 @@ __global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long
     if (tid < 80) (&prof_acc[0][0])[tid] = 0;
     __syncthreads();
     long long t0 = clock64();
-    block_potrf_lower(S, n, fail, dinv);
+    // 512 threads: the production pair (factor with the inverse built beside it, then W to the lower triangle);
+    // otherwise the separate factor and recursive-doubling inverse
+    if (FUSED) block_potrf_inv(S, n, fail, dinv, T); else block_potrf_lower(S, n, fail, dinv);
     long long t1 = clock64();
-    if (tid < 10) stamps[8 + tid] = prof_acc[tid / 5][tid % 5];          // warps 0 and 1
-    block_trtri_lower_inplace(S, n, T, dinv);
+    if (tid < 80) stamps[8 + tid] = prof_acc[tid / 5][tid % 5];          // all warps
+    if (FUSED) block_w_to_lower(S, n, dinv); else block_trtri_lower_inplace(S, n, T, dinv);
     __syncthreads();
     long long t2 = clock64();
     // reload, then 16 diagonal factors back to back on warp 0 (values are garbage after the first; timing only)
@@ -195,7 +198,7 @@ int main() {
     for (int i = 0; i < n * n; ++i) G[i] = sin(0.37 * i) ;
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k < n; ++k) s += G[i * n + k] * G[j * n + k]; A[i * n + j] = s / n + (i == j ? 0.5 : 0.0); }
     double *dA, *dO; long long* dS;
-    cudaMalloc(&dA, n * n * 8); cudaMalloc(&dO, n * n * 8); cudaMalloc(&dS, 64 * 8);
+    cudaMalloc(&dA, n * n * 8); cudaMalloc(&dO, n * n * 8); cudaMalloc(&dS, 128 * 8);
     cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     size_t smem = (128 * SLD + 64 * TLD + DINV_DOUBLES + 16) * 8;
     cudaFuncSetAttribute(prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -204,15 +207,21 @@ int main() {
         long long st[7]; cudaMemcpy(st, dS, 56, cudaMemcpyDeviceToHost);
         printf("threads %d cycles: load %lld potrf %lld [a %lld b %lld c %lld] trtri %lld store %lld (err %s)\n", threads, st[0], st[1], st[4], st[5], st[6], st[2], st[3], cudaGetErrorString(cudaGetLastError()));
     }
-    cudaFuncSetAttribute(prof2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int threads : {256, 512}) {
-        for (int rep = 0; rep < 2; ++rep) prof2_kernel<<<1, threads, smem>>>(dA, n, dS);
+    cudaFuncSetAttribute(prof2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(prof2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int cfg = 0; cfg < 3; ++cfg) {
+        const int threads = cfg == 0 ? 256 : 512, fused = cfg == 2;
+        for (int rep = 0; rep < 2; ++rep) {
+            if (fused) prof2_kernel<1><<<1, threads, smem>>>(dA, n, dS); else prof2_kernel<0><<<1, threads, smem>>>(dA, n, dS);
+        }
         long long st[6]; cudaMemcpy(st, dS, 48, cudaMemcpyDeviceToHost);
-        printf("current, threads %d cycles: potrf %lld trtri %lld | 16 diag factors %lld, panel product(p=0) %lld, trailing(p=0) %lld, syncthreads %lld (err %s)\n",
-               threads, st[0], st[1], st[2], st[3], st[4], st[5], cudaGetErrorString(cudaGetLastError()));
-        long long pa[10]; cudaMemcpy(pa, dS + 8, 80, cudaMemcpyDeviceToHost);
-        printf("  potrf phases, warp 0: head %lld panel0 %lld tile0-update %lld diag %lld sync-wait %lld | warp 1: head %lld panel %lld barrier %lld trailing %lld sync-wait %lld\n",
-               pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], pa[6], pa[7], pa[8], pa[9]);
+        printf("%s, threads %d cycles: potrf %lld %s %lld | 16 diag factors %lld, panel product(p=0) %lld, trailing(p=0) %lld, syncthreads %lld (err %s)\n",
+               fused ? "fused factor + inverse" : "separate factor, inverse", threads, st[0], fused ? "W-to-lower" : "trtri", st[1], st[2], st[3], st[4], st[5],
+               cudaGetErrorString(cudaGetLastError()));
+        long long pa[80]; cudaMemcpy(pa, dS + 8, 640, cudaMemcpyDeviceToHost);
+        printf("  potrf phases, warp 0: head %lld panel0 %lld tile0-update %lld diag %lld sync-wait %lld\n", pa[0], pa[1], pa[2], pa[3], pa[4]);
+        for (int w = 1; w < threads / 32; ++w)
+            printf("    warp %2d: head %lld panel %lld barrier %lld trailing %lld sync-wait %lld\n", w, pa[5 * w], pa[5 * w + 1], pa[5 * w + 2], pa[5 * w + 3], pa[5 * w + 4]);
     }
     lat_kernel<<<1, 32>>>(dS, 1.3);
     long long l[7]; cudaMemcpy(l, dS, 56, cudaMemcpyDeviceToHost);
