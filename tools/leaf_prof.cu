@@ -6,8 +6,9 @@
 // per-warp phase accumulators of block_potrf_lower: [warp][0..4] = loop head, panel tile(s), barrier /
 // tile-0 update, trailing update / diagonal factor, end-of-step sync wait
 __shared__ long long prof_acc[16][5];
-#define GPB_POTRF_DECL long long t_last_ = clock64();
-#define GPB_POTRF_STAMP(i) { if ((threadIdx.x & 31) == 0) { const long long t_now_ = clock64(); prof_acc[threadIdx.x >> 5][i] += t_now_ - t_last_; t_last_ = t_now_; } }
+__shared__ int prof_step[16][16][5];   // the same per step (step index advances at stamp 4)
+#define GPB_POTRF_DECL long long t_last_ = clock64(); int step_ = 0;
+#define GPB_POTRF_STAMP(i) { if ((threadIdx.x & 31) == 0) { const long long t_now_ = clock64(); prof_acc[threadIdx.x >> 5][i] += t_now_ - t_last_; prof_step[threadIdx.x >> 5][step_ & 15][i] += (int)(t_now_ - t_last_); t_last_ = t_now_; } if (i == 4) ++step_; }
 #include "../portfoliooptgp_b200/csrc/block_chol.cuh"
 using namespace gpb;
 namespace gpb {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long
     const int g = lane >> 2, q = lane & 3;
     for (int idx = tid; idx < n * 128; idx += nt) { int i = idx >> 7, j = idx & 127; if (j < n) S[i * SLD + j] = (j <= i) ? A[i * n + j] : 0.0; }
     if (tid < 80) (&prof_acc[0][0])[tid] = 0;
+    for (int e = tid; e < 16 * 16 * 5; e += nt) (&prof_step[0][0][0])[e] = 0;
     __syncthreads();
     long long t0 = clock64();
     // 512 threads: the production pair (factor with the inverse built beside it, then W to the lower triangle);
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(512) prof2_kernel(const double* A, int n, long
     if (FUSED) block_potrf_inv(S, n, fail, dinv, T); else block_potrf_lower(S, n, fail, dinv);
     long long t1 = clock64();
     if (tid < 80) stamps[8 + tid] = prof_acc[tid / 5][tid % 5];          // all warps
+    for (int e = tid; e < 16 * 16 * 5; e += nt) stamps[128 + e] = (&prof_step[0][0][0])[e];
     if (FUSED) block_w_to_lower(S, n, dinv); else block_trtri_lower_inplace(S, n, T, dinv);
     __syncthreads();
     long long t2 = clock64();
@@ -198,7 +201,7 @@ int main() {
     for (int i = 0; i < n * n; ++i) G[i] = sin(0.37 * i) ;
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k < n; ++k) s += G[i * n + k] * G[j * n + k]; A[i * n + j] = s / n + (i == j ? 0.5 : 0.0); }
     double *dA, *dO; long long* dS;
-    cudaMalloc(&dA, n * n * 8); cudaMalloc(&dO, n * n * 8); cudaMalloc(&dS, 128 * 8);
+    cudaMalloc(&dA, n * n * 8); cudaMalloc(&dO, n * n * 8); cudaMalloc(&dS, (128 + 1280) * 8);
     cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     size_t smem = (128 * SLD + 64 * TLD + DINV_DOUBLES + 16) * 8;
     cudaFuncSetAttribute(prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -222,6 +225,16 @@ int main() {
         printf("  potrf phases, warp 0: head %lld panel0 %lld tile0-update %lld diag %lld sync-wait %lld\n", pa[0], pa[1], pa[2], pa[3], pa[4]);
         for (int w = 1; w < threads / 32; ++w)
             printf("    warp %2d: head %lld panel %lld barrier %lld trailing %lld sync-wait %lld\n", w, pa[5 * w], pa[5 * w + 1], pa[5 * w + 2], pa[5 * w + 3], pa[5 * w + 4]);
+        if (threads == 512) {
+            std::vector<long long> ps(1280); cudaMemcpy(ps.data(), dS + 128, 1280 * 8, cudaMemcpyDeviceToHost);
+            printf("    per step, warp 0 waiting (head + sync-wait) | chain (panel0 + tile0 + diag) | longest 'trailing' phase of the other warps:\n");
+            for (int k = 0; k < 15; ++k) {
+                long long mx = 0; int mw = 0;
+                for (int w = 1; w < 16; ++w) { const long long v = ps[(w * 16 + k) * 5 + 3]; if (v > mx) { mx = v; mw = w; } }
+                printf("      k=%2d  wait %5lld  chain %5lld  | max trailing %5lld (warp %d), panel phase of warp 1 %lld\n", k, ps[k * 5 + 0] + ps[k * 5 + 4],
+                       ps[k * 5 + 1] + ps[k * 5 + 2] + ps[k * 5 + 3], mx, mw, ps[(16 + k) * 5 + 1]);
+            }
+        }
     }
     lat_kernel<<<1, 32>>>(dS, 1.3);
     long long l[7]; cudaMemcpy(l, dS, 56, cudaMemcpyDeviceToHost);
