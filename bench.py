@@ -725,7 +725,7 @@ def bench_c5(gpflow, torch, dist, world, rank, barrier, eng, steps=3):
                 pass
     return {"parity_sample": parity, "shard_rows": shard_rows, "workload": "C5: SVGP M=2048, minibatch 65536/GPU, D=8, SquaredExponential, ELBO+grad+Adam step, data-parallel",
             "steps_per_s": 1e3 / ms, "ms_per_step": ms, "rows_per_s": world * B / (ms * 1e-3), "n_gpus": world,
-            "allreduce_doubles": int(tr.flat.numel()), "elbo": elbo,
+            "allreduce_doubles": int(tr.packed.buf.numel()) if tr.packed is not None else 0, "record_doubles": int(tr.flat.numel()), "elbo": elbo,
             "gemm_ms": ms_cat["gemm"] + ms_cat["gemm_small"],
             "gemm_tflops_algorithmic": flops / ((ms_cat["gemm"] + ms_cat["gemm_small"]) * 1e-3) / 1e12,
             "gemm_frac_of_fp64_peak": flops / ((ms_cat["gemm"] + ms_cat["gemm_small"]) * 1e-3) / 1e12 / peaks["fp64_tflops"],

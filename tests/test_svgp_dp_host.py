@@ -112,3 +112,46 @@ def test_unequal_minibatch_sizes_are_rejected_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok and raised for _, ok, raised in outs)
+
+
+def _worker_packed(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from portfoliooptgp_b200.svgp_dp import PackedRecord, allreduce_sum_
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M, D, P = 13, 3, 4
+        head = 2 + P + M * D + M
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = torch.randn(head + M * M, dtype=torch.float64, generator=g)
+        want = flat.clone()
+        allreduce_sum_(want)                                        # the plain, full-size reduction
+        pr = PackedRecord(M, D, P, torch.device("cpu"))
+        got = pr.allreduce_(flat.clone())
+        low = torch.tril(torch.ones(M, M, dtype=torch.bool)).reshape(-1)
+        ok_head = torch.equal(got[:head], want[:head])
+        ok_low = torch.equal(got[head:][low], want[head:][low])
+        untouched = torch.equal(got[head:][~low], flat[head:][~low])   # the strict upper part is not sent
+        q.put((rank, ok_head, ok_low, untouched, pr.buf.numel(), head + M * (M + 1) // 2))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_record_allreduce_equals_full_allreduce_on_the_meaningful_part_gloo_world2():
+    """the q_sqrt gradient crosses the links as its lower triangle (M (M + 1) / 2 doubles)."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, ok_head, ok_low, untouched, n_sent, n_want in outs:
+        assert ok_head and ok_low and untouched
+        assert n_sent == n_want
