@@ -93,6 +93,31 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
             int bi, bj;
             tri_tile(t, bi, bj);
             const int i0 = 2 * bi, j0 = 2 * bj;
+            double v[4];
+            if (!SH::is_static && DP > 8) {
+                // interpreter at D > 8: four coordinate vectors of 16 doubles do not fit the 128-register budget
+                // of a 512-thread CTA (6 KB of spill code, lib/ptxas.log of round 1) -- one element at a time, its
+                // two vectors re-read from shared memory
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {
+                    double xi[DP], xj[DP];
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        xi[d] = xs[(i0 + (e >> 1)) * XSTR + d];
+                        xj[d] = xs[(j0 + (e & 1)) * XSTR + d];
+                    }
+                    v[e] = kernel_value<DP>(kp, xi, xj);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i0 + (e >> 1), j = j0 + (e & 1);
+                    if (i >= N || j >= N) v[e] = (i == j) ? 1.0 : 0.0;   // identity padding
+                    else if (i == j) v[e] += nv;
+                }
+                *reinterpret_cast<double2*>(S + i0 * SLD + j0) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(S + (i0 + 1) * SLD + j0) = make_double2(v[2], v[3]);
+                continue;
+            }
             double xa[DP], xb[DP], xj0[DP], xj1[DP];
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
@@ -101,7 +126,6 @@ batched_gp_kernel(const DevKernel* __restrict__ kps, const int* __restrict__ kba
                 xj0[d] = xs[j0 * XSTR + d];
                 xj1[d] = xs[(j0 + 1) * XSTR + d];
             }
-            double v[4];
             if (fastk) {
                 kernel_value_2x2<DP, SHE>(kp, xa, xb, xj0, xj1, v);
             } else {
