@@ -10,8 +10,8 @@ Same method names, argument order, return values and per-model arithmetic: every
 exactly those of the sequential loop.  What changes is the schedule: each fit runs on its own host thread with
 its own engine handle and CUDA stream (``fit_concurrently``).  A single exact-GP evaluation at these sizes is
 bound by the one-CTA pivot chain of the blocked Cholesky, not by the machine: with four
-C1-size fits in flight the GPU completes 6265 LML+gradient evaluations per second instead of 1996 one after
-the other, at N = 8192 52.0 instead of 47.4 (tools/concurrent_evals.py, profiles/r02_concurrent_evals.json).
+C1-size fits in flight the GPU completes 6686 LML+gradient evaluations per second instead of 2122 one after
+the other, at N = 8192 52.5 instead of 48.4 (tools/concurrent_evals.py, profiles/r02_concurrent_evals.json).
 The reference's loops are sequential; nothing in them depends on the order (each candidate / restart gets its
 own kernel object -- candidates that SHARE a kernel instance are fitted one after the other, in list order,
 as the reference does).
