@@ -408,6 +408,10 @@ def run_gpu(args):
         except Exception as e:
             extras["c2_concurrent_models"] = {"error": repr(e)[:300]}
         try:
+            extras["c3_long_windows"] = bench_c3_long_windows(gpflow, torch)
+        except Exception as e:
+            extras["c3_long_windows"] = {"error": repr(e)[:300]}
+        try:
             extras["c4_large_gp"] = bench_c4(gpflow, torch)
         except Exception as e:
             extras["c4_large_gp"] = {"error": repr(e)[:300]}
@@ -606,6 +610,45 @@ def bench_c3(gpflow, torch, dist, world, rank, barrier, iters=10):
             "fit_converged_fraction": conv, "parity_sample": parity,
             "fit_host_workers": nw,
             "fit_note": "lock-step SciPy L-BFGS-B on the host (bit-identical iterates; worker processes for the SciPy state machines when the shard has >= 512 GPs), LML+grad on the device"}
+
+
+def bench_c3_long_windows(gpflow, torch, B=64, N=256, D=8, reps=3):
+    """The rolling re-fit for windows LONGER than the 128 rows of the one-GP-per-CTA path (the reference's loop,
+    Multi-Input_GPR/main.py:414-456, grows its window by one row per test day): BatchedGPR routes them through
+    gpb_gpr_lml_grad_many -- the blocked single-GP path, several evaluations side by side.  LML+grad evaluations
+    per second on 64 GPs of 256 rows, and two of them against the CPU oracle."""
+    X, Y = make_c2(seed=300, n=N + B - 1, d=D)
+    Xb = np.stack([X[i:i + N] for i in range(B)]); Yb = np.stack([Y[i:i + N, 0] for i in range(B)])
+    K = gpflow.kernels
+    k = K.Exponential(active_dims=slice(0, D - 1), lengthscales=1.3) * K.Exponential(active_dims=slice(D - 1, D), variance=0.8)
+    m = gpflow.BatchedGPR(Xb, Yb, k, noise_variance=1e-2)
+    lml, gth, gnz, info = m.lml_and_grads()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m.lml_and_grads()
+    dt = (time.perf_counter() - t0) / reps
+    out = {"workload": f"{B} GPs x (N={N}, D={D}), Exponential*Exponential, LML+grad through gpb_gpr_lml_grad_many",
+           "handles_side_by_side": len(m._engines), "gp_evals_per_s": B / dt, "ms_per_batch": 1e3 * dt, "all_pd": bool(np.all(info == 0))}
+    try:
+        from oracle import gpflow_oracle as O
+        O.set_distance_form("direct")
+        ko = O.Product([O.Leaf("exponential", active_dims=slice(0, D - 1)), O.Leaf("exponential", active_dims=slice(D - 1, D))])
+        wl, wg = 0.0, 0.0
+        for b in (0, B - 1):
+            O.set_theta(ko, m.theta[b])
+            l0, g0, n0 = O.gpr_lml_and_grad(ko, Xb[b], Yb[b][:, None], float(m.noise[b]))
+            wl = max(wl, abs(lml[b] - l0) / abs(l0))
+            wg = max(wg, float(np.max(np.abs(np.concatenate([gth[b] - g0, [gnz[b] - n0]]))) / max(1.0, np.max(np.abs(g0)))))
+        out["parity_sample"] = {"sampled_gps": 2, "lml_max_rel_diff_vs_oracle": wl, "grad_max_rel_to_max_diff_vs_oracle": wg}
+    except Exception as e:
+        out["parity_sample"] = {"error": repr(e)[:200]}
+    finally:
+        try:
+            O.set_distance_form("gram")
+        except Exception:
+            pass
+    return out
 
 
 def bench_c2_concurrent(gpflow, torch, kernel, evals=6):

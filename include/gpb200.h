@@ -192,6 +192,23 @@ int gpb_gpr_predict_f_reuse(gpb_handle* h, const double* h_theta, double noise_v
                             int64_t factor_serial, const double* d_Xs, int64_t Ns, double* d_mean,
                             double* d_var);
 
+/* MANY independent exact GPs of any size in flight on one GPU: njobs evaluations (gpb_gpr_set_data +
+ * gpb_gpr_lml_grad, or gpb_gpr_lml when want_grad == 0) distributed over nh handles of the same device, one
+ * host thread per handle (job j runs on handle j % nh; the handles need their own streams and the same kernel
+ * expression set).  A single evaluation at N = 129 .. ~2000 is bound by the one-CTA chain of its blocked
+ * factorisation and leaves the machine idle; nh of them side by side fill it.  This is the rolling re-fit of
+ * Multi-Input_GPR/main.py:414-456 for windows longer than the 128 rows of the one-GP-per-CTA path (the loop's
+ * windows grow by one row per test day), and the restart / candidate loops of models/model_trainer.py:26-48,
+ * GPR/model_trainer.py:10-26 without a host thread of the caller per fit.
+ * d_X[j] [N[j], D], d_Yc[j] [N[j]] device pointers; h_theta [njobs, P] row-major, h_noise [njobs];
+ * outputs h_lml [njobs], h_grad_theta [njobs, P], h_grad_noise [njobs] (ignored when want_grad == 0),
+ * h_rc [njobs] = the return code of job j (0 ok, > 0 first non-positive pivot, < 0 error: gpb_last_error of
+ * handle j % nh).  Returns 0 when every job ran (whatever its own code), < 0 on bad arguments. */
+int gpb_gpr_lml_grad_many(int nh, gpb_handle* const* handles, int64_t njobs, const double* const* d_X,
+                          const int64_t* N, int D, const double* const* d_Yc, const double* h_theta, int P,
+                          const double* h_noise, int want_grad, double* h_lml, double* h_grad_theta,
+                          double* h_grad_noise, int* h_rc);
+
 /* d_alpha [N] <- (K + noise I)^-1 (Y - m(X)) of the last gpb_gpr_lml / gpb_gpr_lml_grad / gpb_gpr_predict_f
  * evaluation on this handle (= dLML/dm(X); lets the host layer train mean-function parameters,
  * test_scripts/GPFlow.py:186-190 uses Constant / Linear mean functions).  Asynchronous. */

@@ -87,6 +87,8 @@ SIGNATURES = {
     "gpb_gpr_lml": (_INT, [_P, _DP, _D, _DP]),
     "gpb_gpr_lml_grad": (_INT, [_P, _DP, _D, _DP, _DP, _DP]),
     "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
+    "gpb_gpr_lml_grad_many": (_INT, [_INT, C.POINTER(_P), _I64, C.POINTER(_P), C.POINTER(_I64), _INT, C.POINTER(_P), _DP, _INT,
+                                     _DP, _INT, _DP, _DP, _DP, C.POINTER(_INT)]),
     "gpb_gpr_get_alpha": (_INT, [_P, _P]),
     "gpb_batched_lml_grad": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _P, _INT]),
     "gpb_batched_predict_f": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _INT, _P, _I64, _P, _P, _P]),
@@ -272,6 +274,39 @@ class Engine:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         self._check(self._lib.gpb_gpr_predict_f(self._h, _as_dp(theta), float(noise), _P(dXs), Ns, _P(dmean), _P(dvar)),
                     "gpb_gpr_predict_f")
+
+    @staticmethod
+    def gpr_lml_grad_many(engines, dX: np.ndarray, N: np.ndarray, D: int, dY: np.ndarray, theta: np.ndarray, noise: np.ndarray,
+                          want_grad: bool = True):
+        """``gpb_gpr_lml_grad_many``: job j = (X pointer dX[j], rows N[j], Y pointer dY[j], theta[j], noise[j]) on
+        engine j % len(engines), one host thread of the library per engine.  Returns (lml [J], grad_theta [J,P],
+        grad_noise [J], rc [J]) -- rc > 0: first non-positive pivot of that job; a negative rc raises."""
+        lib = engines[0]._lib
+        nh = len(engines)
+        hs = (_P * nh)(*[e._h for e in engines])
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        J, P = theta.shape
+        if noise.shape != (J,) or len(dX) != J or len(dY) != J or len(N) != J:
+            raise ValueError("gpr_lml_grad_many: one X, Y, N, theta row and noise per job")
+        xs = (_P * J)(*[int(v) for v in dX])
+        ys = (_P * J)(*[int(v) for v in dY])
+        ns = np.ascontiguousarray(N, dtype=np.int64)
+        lml = np.zeros(J)
+        g = np.zeros((J, P))
+        gn = np.zeros(J)
+        rc = np.zeros(J, dtype=np.int32)
+        ret = lib.gpb_gpr_lml_grad_many(nh, hs, J, xs, ns.ctypes.data_as(C.POINTER(_I64)), int(D), ys, _as_dp(theta), int(P),
+                                        _as_dp(noise), int(bool(want_grad)), _as_dp(lml), _as_dp(g), _as_dp(gn),
+                                        rc.ctypes.data_as(C.POINTER(_INT)))
+        if ret != 0:
+            raise EngineError(f"gpb_gpr_lml_grad_many: bad arguments or thread creation failed ({ret})")
+        neg = np.nonzero(rc < 0)[0]
+        if neg.size:
+            j = int(neg[0])
+            msg = lib.gpb_last_error(engines[j % nh]._h)
+            raise EngineError(f"gpb_gpr_lml_grad_many: job {j} failed ({int(rc[j])}): {msg.decode() if msg else ''}")
+        return lml, g, gn, rc
 
     # -- batched small GPs -----------------------------------------------------------------------
     def batched_lml_grad(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dout: int,

