@@ -402,6 +402,10 @@ class BatchedGPR:
         if self._large:
             # windows longer than 128 rows: engines of their own (workspaces, streams) for the side-by-side path
             nh = max(1, min(self.B, int(os.environ.get("GPB_MANY_HANDLES", min(self.MANY_HANDLES, os.cpu_count() or 1)))))
+            # every handle holds its own O(N^2) workspaces (about six N x N fp64 matrices): stay within a quarter
+            # of the free device memory
+            free_bytes, _ = torch.cuda.mem_get_info(self.X.device)
+            nh = max(1, min(nh, int(0.25 * free_bytes / (6.0 * 8.0 * self.N * self.N))))
             self._engines = [_capi.Engine(self.device_index) for _ in range(nh)]
             self._streams = [torch.cuda.Stream(device=self.X.device) for _ in range(nh)]
             for e, st in zip(self._engines, self._streams):
