@@ -401,7 +401,15 @@ class BatchedGPR:
         self._slot_busy = [False]
         if self._large:
             # windows longer than 128 rows: engines of their own (workspaces, streams) for the side-by-side path
-            nh = max(1, min(self.B, int(os.environ.get("GPB_MANY_HANDLES", min(self.MANY_HANDLES, os.cpu_count() or 1)))))
+            ranks_here = 1
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size())))
+            except Exception:
+                pass
+            cores = max(1, (os.cpu_count() or 1) // ranks_here)      # one library thread per handle
+            nh = max(1, min(self.B, int(os.environ.get("GPB_MANY_HANDLES", min(self.MANY_HANDLES, cores)))))
             # every handle holds its own O(N^2) workspaces (about six N x N fp64 matrices): stay within a quarter
             # of the free device memory
             free_bytes, _ = torch.cuda.mem_get_info(self.X.device)
