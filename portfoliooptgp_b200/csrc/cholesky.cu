@@ -119,7 +119,8 @@ static int leaf(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, i
 // info_base: added to the reported pivot index (the block may sit at row info_base of a larger matrix whose
 // diagonal blocks are factorised one by one, factor_L below).
 // ---- the bottom of the recursion as a look-ahead chain -----------------------------------------------------
-// A diagonal block of n <= chain_max() rows (1024): right-looking over its 128-row leaves k = 0 .. nb-1,
+// A diagonal block of n <= chain_limit rows (1024; 2048 inside matrices of 4096 rows or more): right-looking over
+// its 128-row leaves k = 0 .. nb-1,
 //   critical stream:  D_k (leaf: L_kk, W_kk)  ->  P_k  T[k+1:, k] = A[k+1:, k] W_kk^T
 //                                             ->  Sa_k A[k+1:, k+1] -= T[k+1:, k] T[k+1, k]^T   (next leaf's column)
 //   side stream:      Sb_k A[k+2:, k+2:] -= T[k+2:, k] T[k+2:, k]^T ;  R_k  W[k, :k] = -W_kk (T[k, :k] W[:k, :k])
@@ -138,14 +139,25 @@ static cudaEvent_t chain_event(gpb_handle* h, size_t i) {
     return h->chain_events[i];
 }
 
-static int chain_max() {
-    static int v = -1;
-    if (v < 0) {
+// GPB_CHAIN_MAX (tuning knob): fixed size limit of the blocks the chain takes; < 256 switches it off.  Unset: 1024
+// rows, 2048 when the whole matrix has 4096 rows or more (N = 1000 / 2048 / 4096 / 8192 LML+grad: 0.447 / 1.158 /
+// 3.851 / 20.62 ms with 1024, 0.449 / 1.225 / 3.757 / 20.38 with 2048, 4.83 / 22.7 at 4096 / 8192 with 4096).
+static int chain_env() {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("GPB_CHAIN_MAX");
-        v = e ? atoi(e) : 1024;
-        if (v < 2 * NB) v = 0;
+        v = e ? atoi(e) : -1;
+        if (v >= 0 && v < 2 * NB) v = 0;
     }
     return v;
+}
+static int chain_max() {   // upper bound over all matrix sizes (scratch sizing)
+    const int e = chain_env();
+    return e >= 0 ? e : 2048;
+}
+static int chain_limit(int64_t total_rows) {
+    const int e = chain_env();
+    return e >= 0 ? e : (total_rows >= 4096 ? 2048 : 1024);
 }
 
 static int factor_inv_chain(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
@@ -229,7 +241,7 @@ static int factor_inv_chain(gpb_handle* h, double* A, int64_t lda, double* W, in
 static int factor_inv_rec(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, int o, int n, double* logdiag,
                           int* info, bool keepL, double* scratchU, int depth, int info_base = 0) {
     if (n <= NB) return leaf(h, A, lda, W, ldw, n, o, logdiag, info, keepL, info_base);
-    if (h->use_chain && n <= chain_max()) return factor_inv_chain(h, A, lda, W, ldw, o, n, logdiag, info, keepL, scratchU, depth, info_base);
+    if (h->use_chain && n <= h->chain_limit) return factor_inv_chain(h, A, lda, W, ldw, o, n, logdiag, info, keepL, scratchU, depth, info_base);
     const int n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1, o2 = o + n1;
     int rc = factor_inv_rec(h, A, lda, W, ldw, o, n1, logdiag, info, keepL, scratchU, depth + 1, info_base);
     if (rc) return rc;
@@ -322,6 +334,7 @@ int factor_inv(gpb_handle* h, double* A, int64_t lda, double* W, int64_t ldw, in
     }
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) return check_cuda(h, e, "memset info");
+    h->chain_limit = chain_limit(N);
     return factor_inv_rec(h, A, lda, W, ldw, 0, (int)N, logdiag, d_info, keepL, scratch, 0);
 }
 
@@ -395,6 +408,7 @@ int factor_inv_pipelined(gpb_handle* h, double* A, int64_t lda, double* W, int64
         cudaError_t e_ = (call);                            \
         if (e_ != cudaSuccess) return check_cuda(h, e_, what); \
     } while (0)
+    h->chain_limit = chain_limit(b);
     // D_0 on the caller's stream (whole device)
     if ((rc = factor_inv_rec(h, A, lda, W, ldw, 0, size(0), logdiag, d_info, false, nullptr, 0))) return rc;
     GPB_CU(cudaEventRecord(ev_start, S0), "pipeline start record");
@@ -551,6 +565,7 @@ int factor_L(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, dou
     }
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) return check_cuda(h, e, "memset info");
+    h->chain_limit = chain_limit(NBD);      // the diagonal blocks of this path have NBD rows
     return potrf_rec(h, A, lda, Lw, ldl, Wd, 0, (int)N, logdiag, d_info, scratch);
 }
 

@@ -41,7 +41,8 @@ struct gpb_handle {
     // partition and of the small critical-chain partition; gpb_set_option(h, 4, x) switches the pipeline
     bool part_ok = false;
     bool part_tried = false;
-    bool use_chain = true;      // gpb_set_option(h, 5, x): look-ahead chain over the 128-row leaves of a <= 1024-row diagonal block
+    bool use_chain = true;      // gpb_set_option(h, 5, x): look-ahead chain over the 128-row leaves of a <= chain_limit-row diagonal block
+    int chain_limit = 1024;    // rows of the largest block the chain takes in the current factorisation (cholesky.cu)
     bool use_pipeline = false;  // measured slower than the recursion (profiles/r02_pipeline_ab.txt): opt-in
     cudaStream_t part_bulk = nullptr, part_crit = nullptr;
     cudaStream_t part_crit_side[MAX_DEPTH] = {};
