@@ -112,7 +112,7 @@ int64_t gpb_launch_count(gpb_handle* h);
  * rank-1024 products run at 0.90 of the recursion's large-K products and the 8 reserved SMs cost 5 %,
  * which outweighs the hidden latency -- 22.8 vs 21.3 ms at N = 8192, profiles/r02_pipeline_ab.txt;
  * silently off when the driver cannot create the partitions).  option 5: the look-ahead chain over the
- * 128-row leaves of every <= 1024-row diagonal block at the bottom of the blocked factorisation
+ * 128-row leaves of every <= 1024-row (2048 inside matrices of >= 4096 rows) diagonal block at the bottom of the blocked factorisation
  * (default 1; 0 = the plain 2 x 2 recursion down to the leaves). */
 int gpb_set_option(gpb_handle* h, int option, int value);
 /* Diagnostics: which straight-line shape (csrc/shapes.cuh, 1-based id) the current expression matches;

@@ -565,7 +565,7 @@ int factor_L(gpb_handle* h, double* A, int64_t lda, double* Lw, int64_t ldl, dou
     }
     cudaError_t e = cudaMemsetAsync(d_info, 0, sizeof(int), h->stream);
     if (e != cudaSuccess) return check_cuda(h, e, "memset info");
-    h->chain_limit = chain_limit(NBD);      // the diagonal blocks of this path have NBD rows
+    h->chain_limit = chain_limit(N);
     return potrf_rec(h, A, lda, Lw, ldl, Wd, 0, (int)N, logdiag, d_info, scratch);
 }
 

@@ -101,7 +101,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 enum BufId { BUF_K = 0, BUF_W = 1, BUF_VEC = 2, BUF_DINV = 3, BUF_PANEL = 4, BUF_RED = 5, BUF_AUX = 6, BUF_AUX2 = 7, BUF_WD = 8 };
-constexpr int GPB_NBD = 1024;   // factor-only path: diagonal blocks of this size carry explicit inverses (cholesky.cu)
+constexpr int GPB_NBD = 2048;   // factor-only path: diagonal blocks of this size carry explicit inverses (cholesky.cu)
 
 // PROF_GEMM: dgemm_kernel launches with the large (128 x 64) tiles -- the throughput-bound products;
 // PROF_GEMM_SMALL: its 64 x 64 / 32 x 32 configurations -- the latency-bound bottom of the factorisation
