@@ -209,6 +209,15 @@ int gpb_gpr_lml_grad_many(int nh, gpb_handle* const* handles, int64_t njobs, con
                           const double* h_noise, int want_grad, double* h_lml, double* h_grad_theta,
                           double* h_grad_noise, int* h_rc);
 
+/* The same for predict_f: job j = gpb_gpr_set_data(d_X[j], N[j], D, d_Yc[j]) + gpb_gpr_predict_f(theta[j], noise[j],
+ * d_Xs[j] [Ns, D]) -> d_mean[j], d_var[j] [Ns] on handle j % nh (Multi-Input_GPR/main.py:434,454: the one-step-ahead
+ * prediction of every re-fitted window).  h_rc [njobs] as above; outputs of a job with h_rc != 0 are undefined.
+ * Every handle's stream is synchronised before the call returns. */
+int gpb_gpr_predict_f_many(int nh, gpb_handle* const* handles, int64_t njobs, const double* const* d_X,
+                           const int64_t* N, int D, const double* const* d_Yc, const double* h_theta, int P,
+                           const double* h_noise, const double* const* d_Xs, int64_t Ns, double* const* d_mean,
+                           double* const* d_var, int* h_rc);
+
 /* d_alpha [N] <- (K + noise I)^-1 (Y - m(X)) of the last gpb_gpr_lml / gpb_gpr_lml_grad / gpb_gpr_predict_f
  * evaluation on this handle (= dLML/dm(X); lets the host layer train mean-function parameters,
  * test_scripts/GPFlow.py:186-190 uses Constant / Linear mean functions).  Asynchronous. */

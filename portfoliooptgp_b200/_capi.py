@@ -87,6 +87,8 @@ SIGNATURES = {
     "gpb_gpr_lml": (_INT, [_P, _DP, _D, _DP]),
     "gpb_gpr_lml_grad": (_INT, [_P, _DP, _D, _DP, _DP, _DP]),
     "gpb_gpr_predict_f": (_INT, [_P, _DP, _D, _P, _I64, _P, _P]),
+    "gpb_gpr_predict_f_many": (_INT, [_INT, C.POINTER(_P), _I64, C.POINTER(_P), C.POINTER(_I64), _INT, C.POINTER(_P), _DP, _INT,
+                                      _DP, C.POINTER(_P), _I64, C.POINTER(_P), C.POINTER(_P), C.POINTER(_INT)]),
     "gpb_gpr_lml_grad_many": (_INT, [_INT, C.POINTER(_P), _I64, C.POINTER(_P), C.POINTER(_I64), _INT, C.POINTER(_P), _DP, _INT,
                                      _DP, _INT, _DP, _DP, _DP, C.POINTER(_INT)]),
     "gpb_gpr_get_alpha": (_INT, [_P, _P]),
@@ -307,6 +309,31 @@ class Engine:
             msg = lib.gpb_last_error(engines[j % nh]._h)
             raise EngineError(f"gpb_gpr_lml_grad_many: job {j} failed ({int(rc[j])}): {msg.decode() if msg else ''}")
         return lml, g, gn, rc
+
+    @staticmethod
+    def gpr_predict_f_many(engines, dX: np.ndarray, N: np.ndarray, D: int, dY: np.ndarray, theta: np.ndarray, noise: np.ndarray,
+                           dXs: np.ndarray, Ns: int, dmean: np.ndarray, dvar: np.ndarray) -> np.ndarray:
+        """``gpb_gpr_predict_f_many``: per-job predict_f side by side; returns rc [J] (> 0: that job's covariance is
+        not positive definite, its outputs are undefined); a negative rc raises.  Synchronous."""
+        lib = engines[0]._lib
+        nh = len(engines)
+        hs = (_P * nh)(*[e._h for e in engines])
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        J, P = theta.shape
+        arr = lambda v: (_P * J)(*[int(x) for x in v])
+        ns = np.ascontiguousarray(N, dtype=np.int64)
+        rc = np.zeros(J, dtype=np.int32)
+        ret = lib.gpb_gpr_predict_f_many(nh, hs, J, arr(dX), ns.ctypes.data_as(C.POINTER(_I64)), int(D), arr(dY), _as_dp(theta), int(P),
+                                         _as_dp(noise), arr(dXs), int(Ns), arr(dmean), arr(dvar), rc.ctypes.data_as(C.POINTER(_INT)))
+        if ret != 0:
+            raise EngineError(f"gpb_gpr_predict_f_many: bad arguments or thread creation failed ({ret})")
+        neg = np.nonzero(rc < 0)[0]
+        if neg.size:
+            j = int(neg[0])
+            msg = lib.gpb_last_error(engines[j % nh]._h)
+            raise EngineError(f"gpb_gpr_predict_f_many: job {j} failed ({int(rc[j])}): {msg.decode() if msg else ''}")
+        return rc
 
     # -- batched small GPs -----------------------------------------------------------------------
     def batched_lml_grad(self, dX: int, dYc: int, dtheta: int, dnoise: int, B: int, N: int, D: int, dout: int,

@@ -605,19 +605,20 @@ class BatchedGPR:
             Xs = Xs.contiguous()
             mean = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
             var = torch.empty((self.B, Ns), dtype=torch.float64, device=dev)
-            torch.cuda.current_stream(dev).synchronize()         # Xs is complete before the engine's stream reads it
-            eng, st = self._engines[0], self._streams[0]
-            for b in range(self.B):
-                eng.gpr_set_data(int(self._xptr[b]), int(self._nr64[b]), self.D, int(self._yptr[b]))
-                try:
-                    eng.gpr_predict_f(self.theta[b], float(self.noise[b]), Xs[b].data_ptr(), Ns, mean[b].data_ptr(), var[b].data_ptr())
-                except _capi.CholeskyError:
-                    # one GP whose covariance is not positive definite does not take the batch down (as on the
-                    # one-GP-per-CTA path): its predictions are NaN
-                    with torch.cuda.stream(st):
-                        mean[b].fill_(float("nan"))
-                        var[b].fill_(float("nan"))
-            st.synchronize()
+            torch.cuda.current_stream(dev).synchronize()         # Xs, mean, var exist before the engines' streams use them
+            esz = Xs.element_size()
+            xs_ptr = np.array([Xs.data_ptr() + b * Ns * self.D * esz for b in range(self.B)], dtype=np.uint64)
+            m_ptr = np.array([mean.data_ptr() + b * Ns * esz for b in range(self.B)], dtype=np.uint64)
+            v_ptr = np.array([var.data_ptr() + b * Ns * esz for b in range(self.B)], dtype=np.uint64)
+            rc = _capi.Engine.gpr_predict_f_many(self._engines, self._xptr, self._nr64, self.D, self._yptr, self.theta, self.noise,
+                                                 xs_ptr, Ns, m_ptr, v_ptr)
+            bad = np.nonzero(rc > 0)[0]
+            if bad.size:
+                # a GP whose covariance is not positive definite does not take the batch down (as on the
+                # one-GP-per-CTA path): its predictions are NaN
+                it = torch.from_numpy(bad.astype(np.int64)).to(dev)
+                mean[it] = float("nan")
+                var[it] = float("nan")
             return mean, var
         eng = self._engine
         ops.sync_stream(eng)

@@ -449,6 +449,41 @@ int gpb_gpr_lml_grad_many(int nh, gpb_handle* const* handles, int64_t njobs, con
     return 0;
 }
 
+int gpb_gpr_predict_f_many(int nh, gpb_handle* const* handles, int64_t njobs, const double* const* d_X, const int64_t* N,
+                           int D, const double* const* d_Yc, const double* h_theta, int P, const double* h_noise,
+                           const double* const* d_Xs, int64_t Ns, double* const* d_mean, double* const* d_var, int* h_rc) {
+    if (nh < 1 || !handles || njobs < 0 || !d_X || !N || !d_Yc || !h_theta || !h_noise || !d_Xs || !d_mean || !d_var || !h_rc ||
+        P < 0 || Ns < 1)
+        return -2;
+    for (int t = 0; t < nh; ++t) {
+        if (!handles[t]) return -2;
+        for (int u = 0; u < t; ++u)
+            if (handles[u] == handles[t]) return -2;
+    }
+    auto run = [&](int t) {
+        gpb_handle* h = handles[t];
+        for (int64_t j = t; j < njobs; j += nh) {
+            int rc = gpb_gpr_set_data(h, d_X[j], N[j], D, d_Yc[j]);
+            if (rc == 0) rc = gpb_gpr_predict_f(h, h_theta + j * P, h_noise[j], d_Xs[j], Ns, d_mean[j], d_var[j]);
+            h_rc[j] = rc;
+        }
+        DeviceGuard guard(h->device);
+        cudaStreamSynchronize(h->stream);
+    };
+    const int nt = (int)(njobs < nh ? njobs : nh);
+    std::vector<std::thread> pool;
+    pool.reserve(nt > 0 ? nt - 1 : 0);
+    try {
+        for (int t = 1; t < nt; ++t) pool.emplace_back(run, t);
+    } catch (...) {
+        for (auto& th : pool) th.join();
+        return -1;
+    }
+    if (nt > 0) run(0);
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
 int64_t gpb_gpr_factor_serial(gpb_handle* h) { return h ? h->fact_serial : -1; }
 
 int gpb_gpr_predict_f_reuse(gpb_handle* h, const double* h_theta, double noise_variance, int64_t factor_serial,

@@ -208,3 +208,7 @@ def test_long_window_fit_equals_per_gp_scipy_fit_and_survives_a_non_pd_member(gp
     m2 = gp.BatchedGPR(Xd, Yd, gp.kernels.SquaredExponential(lengthscales=50.0), noise_variance=np.array([1e-2, 0.0, 1e-2]), train_noise=False)
     lml, gth, gnz, info = m2.lml_and_grads(noise=np.array([1e-2, 0.0, 1e-2]))
     assert info[1] > 0 and info[0] == 0 and info[2] == 0 and np.isfinite(lml[0]) and np.isfinite(lml[2])
+    mean, var = m2.predict_f(Xd[:, :2, :])
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    assert np.all(np.isnan(mean[1])) and np.all(np.isnan(var[1]))
+    assert np.all(np.isfinite(mean[[0, 2]])) and np.all(np.isfinite(var[[0, 2]]))
