@@ -399,6 +399,7 @@ class BatchedGPR:
         # further result sets for the pipelined fit (several part-batches in flight, lockstep_lbfgsb)
         self._more_out = {}
         self._slot_busy = [False]
+        self._executor = None
         if self._large:
             # windows longer than 128 rows: engines of their own (workspaces, streams) for the side-by-side path
             ranks_here = 1
@@ -532,13 +533,18 @@ class BatchedGPR:
         U = np.array(U, dtype=np.float64)
         idx = np.array(idx, dtype=np.int64)
         if self._large:
-            # the side-by-side path returns through host memory: nothing to leave in flight
-            res = self.loss_and_grads_unconstrained(U, idx)
+            # the side-by-side path is a blocking library call (ctypes drops the GIL for its duration): it runs on
+            # one helper thread, so that the caller can advance the SciPy state machines of the other part-batch
+            # meanwhile; one call at a time -- the handles are not shared between calls
+            if self._executor is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="gpb-many")
+            fut = self._executor.submit(self.loss_and_grads_unconstrained, U, idx)
 
             def done():
-                return res
+                return fut.result()
 
-            done.ready = lambda: True
+            done.ready = fut.done
             return done
         theta, noise = self._unpack(U, idx)
         slot = next((s for s, busy in enumerate(self._slot_busy) if not busy), None)
@@ -587,6 +593,8 @@ class BatchedGPR:
             lbfgs_kwargs["workers"] = self.default_workers(self.B)
         U0 = self._pack()
         self.non_pd_evaluations = np.zeros(self.B, dtype=np.int64)
+        # (long windows: two part-batches in flight measured slower -- 0.088 s against 0.072 s for 32 windows of
+        # 200 - 231 rows: each library call then has half the evaluations to spread over its handles; opt-in only)
         pipelined = lbfgs_kwargs.pop("pipelined", self.B >= 64 and not self._large)
         res = lockstep_lbfgsb(self.loss_and_grads_unconstrained, U0, maxiter=maxiter,
                               fun_batch_async=self.loss_and_grads_unconstrained_async if pipelined else None, **lbfgs_kwargs)

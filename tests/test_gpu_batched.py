@@ -202,6 +202,11 @@ def test_long_window_fit_equals_per_gp_scipy_fit_and_survives_a_non_pd_member(gp
         assert r.nit == res[b].nit
         assert abs(r.fun - res[b].fun) <= 1e-6 * max(1.0, abs(r.fun))
         assert np.max(np.abs(r.x - res[b].x)) < 1e-5
+    # two part-batches in flight (the library call on a helper thread beside the SciPy state machines): same iterates
+    mp_ = gp.BatchedGPR(Xb, Yb, gp.kernels.SquaredExponential() + gp.kernels.Linear(), noise_variance=starts, train_noise=True)
+    res_p = mp_.fit(maxiter=25, pipelined=True)
+    for b in range(B):
+        assert res_p[b].nit == res[b].nit and np.array_equal(res_p[b].x, res[b].x)
     # duplicate rows and (almost) no noise: K is singular to working precision for one member
     Xd = Xb.copy(); Xd[1, 1] = Xd[1, 0]
     Yd = Yb.copy()
