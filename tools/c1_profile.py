@@ -16,3 +16,4 @@ t0 = time.perf_counter(); res = fit(); dt = time.perf_counter() - t0
 print(f"fit: {dt*1e3:.1f} ms, nfev {res.nfev}, {dt/res.nfev*1e3:.3f} ms per evaluation")
 pr = cProfile.Profile(); pr.enable(); res = fit(); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+pstats.Stats(pr).sort_stats("cumtime").print_stats(28)
