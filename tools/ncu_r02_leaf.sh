@@ -1,5 +1,8 @@
+#!/bin/bash
+# Leaf evidence of round 2 (B200_PROFILING.md recipe): phase stamps (tools/leaf_prof), plain run, launch list of one C2
+# evaluation, then a --set full capture of two leaf launches of the second evaluation.
 set -u
-cd /root/repo
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 ./tools/leaf_prof > gpurun_out/r02_leaf_phases.txt 2>&1
 python tools/one_eval.py 8192 1 > gpurun_out/r02_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/r02_plain.log; exit 1; }
