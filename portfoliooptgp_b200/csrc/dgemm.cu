@@ -268,6 +268,18 @@ static int gemm_cfg_override() {
     return v;
 }
 
+static int big_min_k() {
+    static int v = -1;
+    if (v < 0) {
+        // products with K at or below it never take the 128 x 64 tiles: the rank-128 updates of the look-ahead chain
+        // are four k-tiles deep, prologue and epilogue dominate a 128 x 64 CTA (N = 8192 LML+grad: 20.45 ms with
+        // them on the large tiles, 20.31 on the 64 x 64 ones; GPB_BIG_MIN_K is the tuning knob)
+        const char* e = getenv("GPB_BIG_MIN_K");
+        v = e ? atoi(e) : 128;
+    }
+    return v;
+}
+
 static int small_stages() {
     static int v = -1;
     if (v < 0) {
@@ -292,7 +304,7 @@ static int launch_layout(gpb_handle* h, const GemmParams& p, cudaStream_t stream
     // DGEMM; k-contiguous operands want BK = 32 (256-byte row segments), m/n-contiguous ones BK = 16.
     const int64_t tm128 = (p.M + 127) / 128;
     const int64_t big_tiles = p.tri ? 2 * tm128 * (tm128 + 1) / 2 : tm128 * ((p.N + 63) / 64);
-    if (big_tiles >= h->sm_count) {
+    if (big_tiles >= h->sm_count && p.K > big_min_k()) {
         if (AKC || BKC) return launch_cfg<128, 64, 32, 32, 64, 2, AKC, BKC>(h, p, stream);
         return launch_cfg<128, 64, 16, 32, 64, 3, AKC, BKC>(h, p, stream);
     }
